@@ -1,0 +1,146 @@
+// fls_map.cu — device-side construction of the iVox map (K8, static/batch form).
+//
+// IVoxMap::AddPoints (src/ivox_map/ivox_map.cpp:122-143 upstream) inserts points one by one into an
+// unordered_map of std::list nodes.  Here a whole cloud is inserted at once:
+//   key (Morton of round(p/res)) -> stable radix sort -> gather -> run-length encode -> scan -> hash insert.
+// The stable sort keeps insertion order inside a voxel, so the k-NN tie order matches a sequential insert.
+// LRU eviction (capacity_) is not emulated: a build that would reach the capacity returns FLS_ERR_CAPACITY
+// (DESIGN.md "Scope"); upstream evicts nothing while size() < capacity_.
+#include <cub/cub.cuh>
+
+#include "fls_ivox.cuh"
+#include "fls_maps.h"
+
+namespace fls {
+
+BuildScratch::BuildScratch() { cudaMallocHost(&h_num_runs, sizeof(int)); }
+BuildScratch::~BuildScratch() {
+    if (h_num_runs) cudaFreeHost(h_num_runs);
+}
+
+namespace {
+
+__global__ void ivox_keys_kernel(const float4* __restrict__ pts, size_t n, float inv_res, unsigned long long* __restrict__ keys,
+                                 unsigned* __restrict__ idx) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pts[i];
+    keys[i] = morton_key(ivox_coord(p.x, inv_res), ivox_coord(p.y, inv_res), ivox_coord(p.z, inv_res));
+    idx[i] = (unsigned)i;
+}
+
+__global__ void gather_kernel(const float4* __restrict__ src, const unsigned* __restrict__ idx, size_t n, float4* __restrict__ dst) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
+__global__ void table_clear_kernel(HashSlot* tab, size_t slots) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < slots) {
+        tab[i].key = kEmptyKey;
+        tab[i].start = 0;
+        tab[i].count = 0;
+    }
+}
+
+// one thread per voxel run: key recomputed from the run's first point
+__global__ void ivox_insert_kernel(const float4* __restrict__ pts_sorted, const unsigned* __restrict__ starts, const unsigned* __restrict__ counts,
+                                   int n_runs, float inv_res, HashSlot* tab, unsigned mask) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_runs) return;
+    const unsigned s = starts[v];
+    const float4 p = pts_sorted[s];
+    const unsigned long long key = pack_key(ivox_coord(p.x, inv_res), ivox_coord(p.y, inv_res), ivox_coord(p.z, inv_res));
+    unsigned h = hash_key(key) & mask;
+    for (;;) {
+        const unsigned long long prev = atomicCAS(&tab[h].key, kEmptyKey, key);
+        if (prev == kEmptyKey || prev == key) {
+            tab[h].start = s;
+            tab[h].count = counts[v];
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+__global__ void repack_kernel(const unsigned char* __restrict__ raw, size_t n, size_t stride, float4* __restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* f = reinterpret_cast<const float*>(raw + i * stride);
+    float4 p;
+    p.x = f[0];
+    p.y = f[1];
+    p.z = f[2];
+    p.w = f[4];  // pcl::PointXYZI keeps intensity at byte 16
+    out[i] = p;
+}
+
+inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+}  // namespace
+
+void launch_repack(const unsigned char* d_raw, size_t n, size_t stride, float4* d_out, cudaStream_t st) {
+    if (n == 0) return;
+    repack_kernel<<<grid_for(n, 256), 256, 0, st>>>(d_raw, n, stride, d_out);
+}
+
+int IvoxMap::append_and_build(const float4* d_new, size_t n_new, long long capacity, cudaStream_t st) {
+    const size_t n_old = n_pts;
+    const size_t n = n_old + n_new;
+    if (n == 0) return FLS_OK;
+    if (n > 0xfffffff0ull) return FLS_ERR_INVALID_ARG;
+    // grow pts_all preserving the old contents
+    if (n > pts_all.cap) {
+        DevBuf<float4> bigger;
+        bigger.reserve(n + n / 2);
+        if (n_old) FLS_CUDA(cudaMemcpyAsync(bigger.p, pts_all.p, n_old * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        FLS_CUDA(cudaStreamSynchronize(st));
+        std::swap(bigger.p, pts_all.p);
+        std::swap(bigger.cap, pts_all.cap);
+    }
+    if (n_new) FLS_CUDA(cudaMemcpyAsync(pts_all.p + n_old, d_new, n_new * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+
+    BuildScratch& sc = scratch;
+    sc.keys.reserve(n);
+    sc.keys_sorted.reserve(n);
+    sc.uniq.reserve(n);
+    sc.idx.reserve(n);
+    sc.idx_sorted.reserve(n);
+    sc.counts.reserve(n);
+    sc.starts.reserve(n);
+    sc.num_runs.reserve(1);
+    pts_sorted.reserve(n);
+
+    ivox_keys_kernel<<<grid_for(n, 256), 256, 0, st>>>(pts_all.p, n, inv_res, sc.keys.p, sc.idx.p);
+    size_t tmp1 = 0, tmp2 = 0, tmp3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp1, sc.keys.p, sc.keys_sorted.p, sc.idx.p, sc.idx_sorted.p, (int)n, 0, 63, st);
+    cub::DeviceRunLengthEncode::Encode(nullptr, tmp2, sc.keys_sorted.p, sc.uniq.p, sc.counts.p, sc.num_runs.p, (int)n, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp3, sc.counts.p, sc.starts.p, (int)n, st);
+    size_t tmp = tmp1 > tmp2 ? tmp1 : tmp2;
+    tmp = tmp > tmp3 ? tmp : tmp3;
+    sc.cub_tmp.reserve(tmp + 256);
+    size_t tb = sc.cub_tmp.cap;
+    FLS_CUDA(cub::DeviceRadixSort::SortPairs(sc.cub_tmp.p, tb, sc.keys.p, sc.keys_sorted.p, sc.idx.p, sc.idx_sorted.p, (int)n, 0, 63, st));
+    gather_kernel<<<grid_for(n, 256), 256, 0, st>>>(pts_all.p, sc.idx_sorted.p, n, pts_sorted.p);
+    tb = sc.cub_tmp.cap;
+    FLS_CUDA(cub::DeviceRunLengthEncode::Encode(sc.cub_tmp.p, tb, sc.keys_sorted.p, sc.uniq.p, sc.counts.p, sc.num_runs.p, (int)n, st));
+    FLS_CUDA(cudaMemcpyAsync(sc.h_num_runs, sc.num_runs.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FLS_CUDA(cudaStreamSynchronize(st));
+    const int runs = *sc.h_num_runs;
+    if (capacity > 0 && (long long)runs >= capacity) return FLS_ERR_CAPACITY;
+    tb = sc.cub_tmp.cap;
+    FLS_CUDA(cub::DeviceScan::ExclusiveSum(sc.cub_tmp.p, tb, sc.counts.p, sc.starts.p, runs, st));
+    size_t slots = 1024;
+    while (slots < 2 * (size_t)runs) slots <<= 1;
+    table.reserve(slots);
+    mask = (unsigned)(slots - 1);
+    table_clear_kernel<<<grid_for(slots, 256), 256, 0, st>>>(table.p, slots);
+    ivox_insert_kernel<<<grid_for(runs, 256), 256, 0, st>>>(pts_sorted.p, sc.starts.p, sc.counts.p, runs, inv_res, table.p, mask);
+    FLS_CUDA(cudaGetLastError());
+    n_pts = n;
+    n_vox = (size_t)runs;
+    launches += 8;
+    return FLS_OK;
+}
+
+}  // namespace fls

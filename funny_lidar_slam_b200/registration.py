@@ -1,0 +1,151 @@
+"""Host-side mirror of the reference's registration plug-in interface, over the C ABI.
+
+`Registration` mirrors RegistrationInterface (include/registration/registration_interface.h:11-20 upstream):
+`Match(cluster, T) -> bool` (T in-out), `AddCloudToLocalMap([cloud, ...])`, `GetFitnessScore(max_range)`.
+`create_matcher(mode_string, ...)` mirrors the factory branches of FrontEnd::InitMatcher
+(src/slam/frontend.cpp:30-88 upstream) keyed by the same mode strings (constant_variable.h:21-25).
+Clouds are numpy float32 arrays: (n,4) packed x,y,z,intensity or (n,8) pcl::PointXYZI records.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi
+from ._abi import FlsConfig, FlsIterLog, FlsMapInfo, FlsMatchStats
+from ._lib import check, lib
+
+
+@dataclass
+class PointcloudCluster:
+    """The members of PointcloudCluster (include/lidar/pointcloud_cluster.h:13-26 upstream) a matcher reads."""
+    ordered_cloud: np.ndarray | None = None
+    planar_cloud: np.ndarray | None = None
+    corner_cloud: np.ndarray | None = None
+    point_depth_vec: np.ndarray | None = None
+    point_col_index_vec: np.ndarray | None = None
+    row_start_index_vec: np.ndarray | None = None
+    row_end_index_vec: np.ndarray | None = None
+    timestamp: int = 0
+    extra: dict = field(default_factory=dict)
+
+
+def _cloud(a):
+    if a is None:
+        return None, 0, 16, None
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] not in (4, 8):
+        raise ValueError("cloud must be (n,4) packed xyzi or (n,8) pcl::PointXYZI records")
+    return a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1] * 4, a
+
+
+class Registration:
+    def __init__(self, cfg: FlsConfig):
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        check(lib().fls_create(C.byref(cfg), C.byref(self._h)), "fls_create")
+        self.last_stats = FlsMatchStats()
+
+    # -- RegistrationInterface ----------------------------------------------------------------------------
+    def AddCloudToLocalMap(self, cloud_list) -> None:
+        if isinstance(cloud_list, np.ndarray):
+            cloud_list = [cloud_list]
+        ptrs, ns, keep, stride = [], [], [], None
+        for c in cloud_list:
+            p, n, s, a = _cloud(c)
+            if stride is not None and s != stride:
+                raise ValueError("all clouds of one call must share a layout")
+            stride = s
+            ptrs.append(p)
+            ns.append(n)
+            keep.append(a)
+        arr_p = (C.c_void_p * len(ptrs))(*ptrs)
+        arr_n = (C.c_size_t * len(ns))(*ns)
+        check(lib().fls_add_cloud(self._h, len(ptrs), arr_p, arr_n, stride), "fls_add_cloud")
+
+    def Match(self, cluster: PointcloudCluster, T: np.ndarray) -> bool:
+        """T: (4,4) float64, updated in place (also on failure, as upstream)."""
+        po, no, so, ko = _cloud(cluster.ordered_cloud)
+        pp, npl, sp, kp = _cloud(cluster.planar_cloud)
+        pc, nc, scn, kc = _cloud(cluster.corner_cloud)
+        strides = {s for s, k in ((so, ko), (sp, kp), (scn, kc)) if k is not None}
+        if len(strides) > 1:
+            raise ValueError("all clouds of one cluster must share a layout")
+        stride = strides.pop() if strides else 16
+        Tc = np.ascontiguousarray(np.asarray(T, np.float64).T).copy()  # Eigen column-major memory
+        conv = C.c_int(0)
+        st = FlsMatchStats()
+        rc = lib().fls_match(self._h, po, no, pp, npl, pc, nc, stride, Tc.ctypes.data_as(C.c_void_p), C.byref(conv), C.byref(st))
+        check(rc, "fls_match")
+        T[...] = Tc.T
+        self.last_stats = st
+        return bool(conv.value)
+
+    def GetFitnessScore(self, max_range: float) -> float:
+        out = C.c_float(0)
+        rc = lib().fls_fitness(self._h, float(max_range), C.byref(out))
+        if rc == _abi.FLS_ERR_UNSUPPORTED:
+            return float(np.finfo(np.float32).max)
+        check(rc, "fls_fitness")
+        return float(out.value)
+
+    # -- device-resident scan (bench `value` leg) ---------------------------------------------------------
+    def match_device(self, d_ptr: int, n: int, T: np.ndarray) -> bool:
+        Tc = np.ascontiguousarray(np.asarray(T, np.float64).T).copy()
+        conv = C.c_int(0)
+        st = FlsMatchStats()
+        check(lib().fls_match_device(self._h, C.c_void_p(d_ptr), n, Tc.ctypes.data_as(C.c_void_p), C.byref(conv), C.byref(st)), "fls_match_device")
+        T[...] = Tc.T
+        self.last_stats = st
+        return bool(conv.value)
+
+    # -- introspection ---------------------------------------------------------------------------------
+    def iter_log(self):
+        cap = max(1, self.cfg.max_iterations)
+        buf = (FlsIterLog * cap)()
+        n = lib().fls_get_iter_log(self._h, buf, cap)
+        if n < 0:
+            check(n, "fls_get_iter_log")
+        return [dict(H=np.array(b.H).reshape(6, 6), g=np.array(b.g), dx=np.array(b.dx), sum_residual=b.sum_residual, n_valid=b.n_valid)
+                for b in buf[:n]]
+
+    def map_info(self) -> FlsMapInfo:
+        mi = FlsMapInfo()
+        check(lib().fls_get_map_info(self._h, C.byref(mi)), "fls_get_map_info")
+        return mi
+
+    def ivox_knn(self, queries: np.ndarray, k: int = 5):
+        p, n, s, keep = _cloud(queries)
+        out = np.zeros((n, k, 4), np.float32)
+        cnt = np.zeros(n, np.int32)
+        check(lib().fls_ivox_knn(self._h, p, n, s, k, out.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)), "fls_ivox_knn")
+        return out, cnt
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().fls_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def create_matcher(mode: str, **params) -> Registration:
+    """Factory keyed by the reference's mode strings ("PointToPlane_IVOX", "IncrementalNDT", "IcpOptimized", ...)."""
+    if mode not in _abi.METHOD_BY_MODE_STRING:
+        raise ValueError(f"unknown registration_and_searcher_mode {mode!r}")
+    return Registration(_abi.default_config(_abi.METHOD_BY_MODE_STRING[mode], **params))
+
+
+def voxel_grid(points: np.ndarray, leaf: float, device: int = 0) -> np.ndarray:
+    """VoxelGridCloud (include/common/pointcloud_utility.h:216-224 upstream) on the device."""
+    p, n, s, keep = _cloud(points)
+    out = np.empty((max(n, 1), 4), np.float32)
+    n_out = C.c_size_t(0)
+    check(lib().fls_voxel_grid(device, p, n, s, float(leaf), out.ctypes.data_as(C.c_void_p), C.byref(n_out)), "fls_voxel_grid")
+    return out[:n_out.value].copy()

@@ -1,0 +1,270 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  parity unpinned (see orc_math.h header).
+//
+// extern "C" surface of the CPU oracle, loaded with ctypes by tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs.  It takes the product's fls_config struct
+// (include/fls_b200.h — interface header only) so a test can hand the same configuration to both
+// sides.  Poses cross this API as Eigen Mat4d memory (16 doubles, column-major).
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/fls_b200.h"
+#include "orc_cloud.h"
+#include "orc_features.h"
+#include "orc_ivox.h"
+#include "orc_math.h"
+#include "orc_reg.h"
+
+using namespace orc;
+
+namespace {
+
+Cloud load_cloud(const void* pts, size_t n, size_t stride) {
+    Cloud c(n);
+    const unsigned char* b = static_cast<const unsigned char*>(pts);
+    const size_t ioff = (stride >= 32) ? 16 : 12;
+    for (size_t k = 0; k < n; ++k) {
+        const float* f = reinterpret_cast<const float*>(b + k * stride);
+        c[k].x = f[0]; c[k].y = f[1]; c[k].z = f[2];
+        std::memcpy(&c[k].i, b + k * stride + ioff, 4);
+    }
+    return c;
+}
+void col2row(const double* c, double* r) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) r[i * 4 + j] = c[j * 4 + i];
+}
+void row2col(const double* r, double* c) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) c[j * 4 + i] = r[i * 4 + j];
+}
+
+struct Reg {
+    fls_config cfg;
+    std::unique_ptr<LoamP2PlaneIvox> p2p;
+    std::unique_ptr<IncrementalNdt> ndt;
+    std::unique_ptr<IcpOptimized> icp;
+    MatchResult last;
+};
+
+}  // namespace
+
+extern "C" {
+
+int orc_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+// ---- math KAT hooks -------------------------------------------------------------------------------
+void orc_so3_exp(const double* v, double* R) { so3_exp(v, R); }
+void orc_se3_exp(const double* v, double* T) { se3_exp(v, T); }
+void orc_rot_to_rpy(const double* R, double* rpy) { rot_to_rpy(R, rpy); }
+float orc_fast_atan2f(float y, float x) { return fast_atan2f(y, x); }
+void orc_lstsq53(const double* A, const double* b, double* x) { lstsq_colpiv_qr<5, 3>(A, b, x); }
+void orc_solve6_fullpiv(const double* H, const double* g, double* x) { solve_fullpiv<6>(H, g, x); }
+double orc_solve6_lu(const double* H, const double* g, double* x) { return solve_lu<6>(H, g, x); }
+void orc_sym_eig3(const double* S, double* lam, double* V) { sym_eig3(S, lam, V); }
+void orc_inv3(const double* A, double* Ai) { inv3(A, Ai); }
+
+// ---- cloud primitives -----------------------------------------------------------------------------
+size_t orc_voxel_grid(const void* pts, size_t n, size_t stride, float leaf, float* out) {
+    const Cloud o = voxel_grid(load_cloud(pts, n, stride), leaf);
+    std::memcpy(out, o.data(), o.size() * sizeof(P4));
+    return o.size();
+}
+void orc_transform_d(const float* pts, size_t n, const double* T_col, float* out) {
+    double T[16];
+    col2row(T_col, T);
+    for (size_t k = 0; k < n; ++k) {
+        const P4 o = transform_point_d(P4{pts[k * 4], pts[k * 4 + 1], pts[k * 4 + 2], pts[k * 4 + 3]}, T);
+        std::memcpy(out + k * 4, &o, sizeof(P4));
+    }
+}
+void orc_transform_f(const float* pts, size_t n, const double* T_col, float* out) {
+    double T[16];
+    col2row(T_col, T);
+    const Cloud o = transform_cloud_f(load_cloud(pts, n, 16), T);
+    std::memcpy(out, o.data(), o.size() * sizeof(P4));
+}
+
+void* orc_knn_build(const float* pts, size_t n, float cell) {
+    auto* t = new ExactKnn();
+    t->build(load_cloud(pts, n, 16), cell);
+    return t;
+}
+void orc_knn_search(void* h, const float* q, size_t nq, int k, int* idx, float* d2, int* found) {
+    auto* t = static_cast<ExactKnn*>(h);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < int64_t(nq); ++i) {
+        const P4 qq{q[i * 4], q[i * 4 + 1], q[i * 4 + 2], q[i * 4 + 3]};
+        found[i] = t->search(qq, k, idx + i * k, d2 + i * k);
+    }
+}
+void orc_knn_free(void* h) { delete static_cast<ExactKnn*>(h); }
+
+// ---- iVox -----------------------------------------------------------------------------------------
+void* orc_ivox_create(float res, int nearby, size_t capacity) { return new IVox(res, nearby, capacity); }
+void orc_ivox_add(void* h, const float* pts, size_t n) { static_cast<IVox*>(h)->add_points(load_cloud(pts, n, 16)); }
+void orc_ivox_closest(void* h, const float* q, size_t nq, int K, float max_range, float* out, int* found) {
+    auto* iv = static_cast<IVox*>(h);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < int64_t(nq); ++i) {
+        const P4 qq{q[i * 4], q[i * 4 + 1], q[i * 4 + 2], q[i * 4 + 3]};
+        P4 tmp[16];
+        const int f = iv->closest(qq, K, max_range, tmp);
+        found[i] = f;
+        std::memset(out + i * K * 4, 0, sizeof(float) * 4 * K);
+        std::memcpy(out + i * K * 4, tmp, sizeof(P4) * f);
+    }
+}
+size_t orc_ivox_num_voxels(void* h) { return static_cast<IVox*>(h)->num_voxels(); }
+size_t orc_ivox_num_points(void* h) { return static_cast<IVox*>(h)->num_points(); }
+void orc_ivox_free(void* h) { delete static_cast<IVox*>(h); }
+
+// ---- registration plug-ins --------------------------------------------------------------------------
+void* orc_reg_create(const fls_config* c) {
+    auto* r = new Reg();
+    r->cfg = *c;
+    switch (c->method) {
+        case FLS_P2PLANE_IVOX:
+            r->p2p.reset(new LoamP2PlaneIvox(c->point_to_planar_thres, c->position_converge_thres, c->rotation_converge_thres,
+                                             unsigned(c->max_iterations), c->localization_mode != 0, c->ivox_resolution, c->ivox_nearby,
+                                             size_t(c->ivox_capacity)));
+            break;
+        case FLS_NDT:
+            r->ndt.reset(new IncrementalNdt(c->ndt_voxel_size, c->ndt_outlier_thres, c->source_cloud_filter_size, c->rotation_converge_thres,
+                                            c->position_converge_thres, c->ndt_min_points_in_voxel, c->ndt_max_points_in_voxel,
+                                            c->ndt_min_effective_pts, c->ndt_capacity, c->max_iterations, c->localization_mode != 0));
+            break;
+        case FLS_ICP_P2P:
+            r->icp.reset(new IcpOptimized(unsigned(c->max_iterations), unsigned(c->local_map_size), c->map_cloud_filter_size,
+                                          c->source_cloud_filter_size, c->icp_max_correspond_distance, c->position_converge_thres,
+                                          c->rotation_converge_thres, c->rot_thre_add_cloud, c->dist_thre_add_cloud, c->localization_mode != 0));
+            break;
+        default:
+            delete r;
+            return nullptr;
+    }
+    return r;
+}
+void orc_reg_free(void* h) { delete static_cast<Reg*>(h); }
+
+int orc_reg_add_cloud(void* h, const void* pts, size_t n, size_t stride) {
+    auto* r = static_cast<Reg*>(h);
+    const Cloud c = load_cloud(pts, n, stride);
+    if (r->p2p) r->p2p->add_cloud(c);
+    else if (r->ndt) r->ndt->add_cloud(c);
+    else if (r->icp) r->icp->add_cloud(c);
+    return 0;
+}
+
+// returns wall seconds spent inside Match (steady_clock) through *seconds
+int orc_reg_match(void* h, const void* pts, size_t n, size_t stride, double* T_col, int* converged, fls_match_stats* st, double* seconds) {
+    auto* r = static_cast<Reg*>(h);
+    const Cloud c = load_cloud(pts, n, stride);
+    double T[16];
+    col2row(T_col, T);
+    const auto t0 = std::chrono::steady_clock::now();
+    if (r->p2p) r->last = r->p2p->match(c, T);
+    else if (r->ndt) r->last = r->ndt->match(c, T);
+    else r->last = r->icp->match(c, T);
+    const auto t1 = std::chrono::steady_clock::now();
+    row2col(T, T_col);
+    if (converged) *converged = r->last.converged ? 1 : 0;
+    if (st) {
+        std::memset(st, 0, sizeof(*st));
+        st->iterations = r->last.iters;
+        st->converged = r->last.converged;
+        st->n_valid = r->last.n_valid;
+        st->sum_residual = r->last.sum_res;
+        st->n_source = int64_t(n);
+    }
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    return 0;
+}
+int orc_reg_get_iter_log(void* h, fls_iter_log* out, int cap) {
+    auto* r = static_cast<Reg*>(h);
+    const int n = std::min<int>(cap, int(r->last.log.size()));
+    for (int i = 0; i < n; ++i) {
+        std::memcpy(out[i].H, r->last.log[i].H, sizeof(out[i].H));
+        std::memcpy(out[i].g, r->last.log[i].g, sizeof(out[i].g));
+        std::memcpy(out[i].dx, r->last.log[i].dx, sizeof(out[i].dx));
+        out[i].sum_residual = r->last.log[i].sum_res;
+        out[i].n_valid = r->last.log[i].n_valid;
+    }
+    return n;
+}
+float orc_reg_fitness(void* h, float max_range) {
+    auto* r = static_cast<Reg*>(h);
+    if (r->p2p) return r->p2p->fitness(max_range);
+    if (r->ndt) return r->ndt->fitness(max_range);
+    return r->icp->fitness(max_range);
+}
+size_t orc_reg_map_voxels(void* h) {
+    auto* r = static_cast<Reg*>(h);
+    if (r->p2p) return r->p2p->ivox().num_voxels();
+    if (r->ndt) return r->ndt->num_voxels();
+    return r->icp->map().size();
+}
+size_t orc_reg_map_points(void* h) {
+    auto* r = static_cast<Reg*>(h);
+    if (r->p2p) return r->p2p->ivox().num_points();
+    if (r->icp) return r->icp->map().size();
+    return 0;
+}
+// NDT voxel dump: returns count; arrays sized by orc_reg_map_voxels
+size_t orc_reg_ndt_dump(void* h, int* keys, double* mu, double* info, int* est) {
+    auto* r = static_cast<Reg*>(h);
+    if (!r->ndt) return 0;
+    std::vector<int> k, e;
+    std::vector<double> m, i;
+    r->ndt->dump(k, m, i, e);
+    std::memcpy(keys, k.data(), k.size() * sizeof(int));
+    std::memcpy(mu, m.data(), m.size() * sizeof(double));
+    std::memcpy(info, i.data(), i.size() * sizeof(double));
+    std::memcpy(est, e.data(), e.size() * sizeof(int));
+    return e.size();
+}
+
+// ---- LOAM features ----------------------------------------------------------------------------------
+// project(): returns N (ordered points); outputs sized V*H (depth, col), V (row_start/end), ordered V*H*4 floats
+size_t orc_project(const float* raw, const int* ring, size_t n, int V, int H, float h_res, float min_d, float max_d, float* ordered, float* depth,
+                   int* col, int* row_start, int* row_end) {
+    std::vector<int> rg(ring, ring + n);
+    const Projected p = project(load_cloud(raw, n, 16), rg, V, H, h_res, min_d, max_d);
+    std::memcpy(ordered, p.ordered.data(), p.ordered.size() * sizeof(P4));
+    std::memcpy(depth, p.depth.data(), p.depth.size() * sizeof(float));
+    std::memcpy(col, p.col.data(), p.col.size() * sizeof(int));
+    std::memcpy(row_start, p.row_start.data(), V * sizeof(int));
+    std::memcpy(row_end, p.row_end.data(), V * sizeof(int));
+    return p.ordered.size();
+}
+int orc_extract_features(const float* depth, const int* col, size_t n, const int* row_start, const int* row_end, int V, float corner_thr,
+                         float planar_thr, int* corner_idx, size_t* n_corner, int* planar_idx, size_t* n_planar, double* seconds) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const Features f = extract_features(int(n), depth, col, V, row_start, row_end, corner_thr, planar_thr);
+    const auto t1 = std::chrono::steady_clock::now();
+    std::memcpy(corner_idx, f.corner_idx.data(), f.corner_idx.size() * sizeof(int));
+    std::memcpy(planar_idx, f.planar_idx.data(), f.planar_idx.size() * sizeof(int));
+    *n_corner = f.corner_idx.size();
+    *n_planar = f.planar_idx.size();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol of include/fls_b200.h."""
+import ctypes as C
+import os
+import re
+
+from funny_lidar_slam_b200 import _abi, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "fls_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fls_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = _header_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), f"libfls_b200.so does not export {n}"
+    assert set(names) == set(_lib.EXPORTS)
+    assert L.fls_abi_version() == _abi.FLS_ABI_VERSION
+
+
+def test_config_default_matches_python_twin():
+    L = _lib.lib()
+    for m in range(5):
+        c = _abi.FlsConfig()
+        assert L.fls_config_default(C.byref(c), m) == 0
+        p = _abi.default_config(m)
+        for name, _ in _abi.FlsConfig._fields_:
+            if name == "reserved":
+                continue
+            assert getattr(c, name) == getattr(p, name), (m, name)
+
+
+def test_struct_sizes_match_header_layout():
+    # layouts are fixed by the C header; these sizes are what gcc produces for it (checked by the build)
+    assert C.sizeof(_abi.FlsMatchStats) == 56
+    assert C.sizeof(_abi.FlsIterLog) == 8 * (36 + 6 + 6 + 1 + 1)
+    assert C.sizeof(_abi.FlsMapInfo) == 32
+
+
+def test_error_strings_and_invalid_args():
+    L = _lib.lib()
+    assert b"no CPU fallback" in L.fls_strerror(_abi.FLS_ERR_NO_DEVICE)
+    assert L.fls_create(None, None) == _abi.FLS_ERR_INVALID_ARG
+    bad = _abi.default_config(_abi.FLS_P2PLANE_IVOX, max_iterations=2147483647)  # IntNaN sentinel upstream
+    h = C.c_void_p()
+    assert L.fls_create(C.byref(bad), C.byref(h)) == _abi.FLS_ERR_INVALID_ARG

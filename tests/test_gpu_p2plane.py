@@ -1,0 +1,107 @@
+"""GPU parity: LoamPointToPlaneIVOX path (K1 + K6) through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from funny_lidar_slam_b200 import FLS_P2PLANE_IVOX, default_config, synth
+from funny_lidar_slam_b200._abi import FLS_FLAG_ITER_LOG
+from tests.conftest import to_pcl
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-4  # metres   (BASELINE.json north_star)
+ROT_TOL = 1e-4  # radians
+
+
+def _pair(cfg):
+    from funny_lidar_slam_b200.registration import Registration
+    from oracle import pyoracle as orc
+    return Registration(cfg), orc.Registration(cfg)
+
+
+def test_ivox_knn_matches_oracle(scene16):
+    from funny_lidar_slam_b200.registration import Registration
+    from oracle import pyoracle as orc
+    cfg = default_config(FLS_P2PLANE_IVOX)
+    g = Registration(cfg)
+    g.AddCloudToLocalMap([scene16["map"]])
+    iv = orc.IVox(0.5, 2, 1000000)
+    iv.add(scene16["map"])
+    mi = g.map_info()
+    assert mi.n_points == len(scene16["map"]) and mi.n_voxels == iv.num_voxels
+    q = synth.transform_points(scene16["scan"], scene16["guess"])[:6000]
+    gp, gc = g.ivox_knn(q)
+    op, oc = iv.closest(q, 5, 5.0)
+    assert np.array_equal(gc, oc)
+    full = gc == 5
+    assert full.sum() > 1000
+    # nearest neighbour identical; the 5-set identical up to ordering of equal-distance ties
+    assert np.array_equal(gp[full][:, 0, :3], op[full][:, 0, :3])
+    gs = np.sort(gp[full][:, :, :3].reshape(full.sum(), -1), axis=1)
+    os_ = np.sort(op[full][:, :, :3].reshape(full.sum(), -1), axis=1)
+    assert np.array_equal(gs, os_)
+
+
+@pytest.mark.parametrize("layout", ["packed", "pcl"])
+def test_match_config1_scene(scene16, layout):
+    cfg = default_config(FLS_P2PLANE_IVOX, flags=FLS_FLAG_ITER_LOG)
+    g, o = _pair(cfg)
+    mp, sc = scene16["map"], scene16["scan"]
+    from funny_lidar_slam_b200.registration import PointcloudCluster
+    if layout == "pcl":
+        g.AddCloudToLocalMap([to_pcl(mp)])
+        cl = PointcloudCluster(planar_cloud=to_pcl(sc))
+    else:
+        g.AddCloudToLocalMap([mp])
+        cl = PointcloudCluster(planar_cloud=sc)
+    o.add_cloud(mp)
+    Tg = scene16["guess"].copy()
+    ok_g = g.Match(cl, Tg)
+    ok_o, To, st_o = o.match(sc, scene16["guess"])
+    st_g = g.last_stats
+    assert ok_g == ok_o
+    assert st_g.iterations == st_o.iterations
+    dt, dr = synth.pose_error(Tg, To)
+    assert dt < POS_TOL and dr < ROT_TOL, (dt, dr)
+    assert abs(st_g.n_valid - st_o.n_valid) <= max(2, st_o.n_valid // 2000)
+    # per-iteration normal equations
+    lg, lo = g.iter_log(), o.iter_log()
+    assert len(lg) == len(lo)
+    H0g, H0o = lg[0]["H"], lo[0]["H"]
+    assert lg[0]["n_valid"] == lo[0]["n_valid"]
+    assert np.allclose(H0g, H0o, rtol=1e-9, atol=1e-6)
+    assert np.allclose(lg[0]["g"], lo[0]["g"], rtol=1e-9, atol=1e-6)
+    # ground truth sanity
+    assert synth.pose_error(Tg, scene16["truth"])[0] < 0.02
+
+
+def test_match_64line(scene64):
+    cfg = default_config(FLS_P2PLANE_IVOX)
+    g, o = _pair(cfg)
+    g.AddCloudToLocalMap([scene64["map"]])
+    o.add_cloud(scene64["map"])
+    from funny_lidar_slam_b200.registration import PointcloudCluster
+    Tg = scene64["guess"].copy()
+    ok_g = g.Match(PointcloudCluster(planar_cloud=scene64["scan"]), Tg)
+    ok_o, To, st_o = o.match(scene64["scan"], scene64["guess"])
+    assert ok_g == ok_o and g.last_stats.iterations == st_o.iterations
+    dt, dr = synth.pose_error(Tg, To)
+    assert dt < POS_TOL and dr < ROT_TOL, (dt, dr)
+
+
+def test_match_failure_paths(scene16):
+    """empty scan / scan far from the map: Match returns false, T still written (loam_point_to_plane_ivox.h:198-203)."""
+    cfg = default_config(FLS_P2PLANE_IVOX)
+    g, o = _pair(cfg)
+    g.AddCloudToLocalMap([scene16["map"]])
+    o.add_cloud(scene16["map"])
+    from funny_lidar_slam_b200.registration import PointcloudCluster
+    far = scene16["guess"].copy()
+    far[:3, 3] += 500.0
+    Tg = far.copy()
+    ok_g = g.Match(PointcloudCluster(planar_cloud=scene16["scan"][:500]), Tg)
+    ok_o, To, _ = o.match(scene16["scan"][:500], far)
+    assert ok_g is False and ok_o is False
+    assert np.allclose(Tg, To, atol=1e-12)
+    Tg = scene16["guess"].copy()
+    assert g.Match(PointcloudCluster(planar_cloud=np.zeros((0, 4), np.float32)), Tg) is False
+    assert np.allclose(Tg, scene16["guess"], atol=1e-12)
