@@ -33,6 +33,7 @@ FLS_NEARBY_CENTER, FLS_NEARBY6, FLS_NEARBY18, FLS_NEARBY26 = 0, 1, 2, 3
 FLS_LAYOUT_PCL_XYZI = 32
 FLS_LAYOUT_PACKED = 16
 FLS_FLAG_ITER_LOG = 1
+FLS_FLAG_PROFILE = 2
 
 
 class FlsConfig(C.Structure):
@@ -56,7 +57,7 @@ class FlsMatchStats(C.Structure):
     _fields_ = [
         ("iterations", C.c_int32), ("converged", C.c_int32), ("n_source", C.c_int64), ("n_valid", C.c_int64),
         ("sum_residual", C.c_double), ("gpu_ms", C.c_float), ("gpu_launches", C.c_int32), ("h2d_bytes", C.c_int64),
-        ("d2h_bytes", C.c_int64),
+        ("d2h_bytes", C.c_int64), ("kernel_ms", C.c_float), ("kernel_launches", C.c_int32), ("algo_bytes", C.c_int64),
     ]
 
 

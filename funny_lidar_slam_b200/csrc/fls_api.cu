@@ -23,6 +23,11 @@ Handle::Handle(const fls_config& c) : cfg(c) {
     FLS_CUDA(cudaMallocHost(&h_state, sizeof(GnState)));
     state.reserve(1);
     ivox.set_resolution(cfg.ivox_resolution);
+    profile = (cfg.flags & FLS_FLAG_PROFILE) != 0;
+    if (profile) {
+        prof_ev.resize(2 * (size_t)(cfg.max_iterations > 0 ? cfg.max_iterations : 1));
+        for (auto& e : prof_ev) FLS_CUDA(cudaEventCreate(&e));
+    }
     if (cfg.flags & FLS_FLAG_ITER_LOG) {
         log_cap = cfg.max_iterations > 0 ? cfg.max_iterations : 1;
         log.reserve(log_cap);
@@ -34,6 +39,7 @@ Handle::~Handle() {
     cudaSetDevice(cfg.device);
     if (stream) cudaStreamSynchronize(stream);
     if (h_state) cudaFreeHost(h_state);
+    for (auto& e : prof_ev) cudaEventDestroy(e);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -128,8 +134,14 @@ int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* co
     gp.n_blocks = grid;
     gp.rot_thres = cfg.rotation_converge_thres;
     gp.pos_thres = cfg.position_converge_thres;
+    // roofline accounting: 16 B source point + n_stencil x 16 B slot probes + 32 B persistent
+    // record per point-iteration, 16 B per map record resident in the hit voxels.
+    per_point_iter_bytes = 16 + 16LL * a.map.n_stencil + 32;
+    per_cand_bytes = 16;
     for (int it = 0; it < cfg.max_iterations; ++it) {
+        if (profile) FLS_CUDA(cudaEventRecord(prof_ev[2 * it], stream));
         launch_p2plane_iter(a, stream);
+        if (profile) FLS_CUDA(cudaEventRecord(prof_ev[2 * it + 1], stream));
         launch_gn_solve(state.p, partials.p, gp, log.p, log_cap, stream);
         launches += (ni > 0 ? 2 : 1);
     }
@@ -161,6 +173,17 @@ int Handle::finish_match(double* T, int* converged, fls_match_stats* st, long lo
         st->n_source = n_source;
         st->n_valid = s.n_valid;
         st->sum_residual = s.sum_res;
+        if (profile) {
+            float tot = 0.f;
+            for (int it = 0; it < s.iter && 2 * it + 1 < (int)prof_ev.size(); ++it) {
+                float ms = 0.f;
+                FLS_CUDA(cudaEventElapsedTime(&ms, prof_ev[2 * it], prof_ev[2 * it + 1]));
+                tot += ms;
+            }
+            st->kernel_ms = tot;
+            st->kernel_launches = s.iter;
+            st->algo_bytes = (long long)s.iter * n_source * per_point_iter_bytes + (long long)(s.cand_total + 0.5) * per_cand_bytes;
+        }
     }
     return FLS_OK;
 }

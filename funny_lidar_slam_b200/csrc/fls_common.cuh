@@ -131,8 +131,10 @@ __device__ __forceinline__ float xform_row_f(float r0, float r1, float r2, float
 #endif
 
 // ---- Gauss-Newton state resident in device memory --------------------------------------------------------
-// 29 reduced quantities per iteration: 21 upper-triangular entries of H, 6 of g, n_valid, sum of residuals.
-static constexpr int kNumAcc = 29;
+// 31 reduced quantities per iteration: 21 upper-triangular entries of H, 6 of g, n_valid, sum of residuals,
+// and two traffic counters for the roofline accounting (map records scanned, table probes that hit).
+static constexpr int kNumAcc = 31;
+static constexpr int kAccValid = 27, kAccRes = 28, kAccCand = 29, kAccHits = 30;
 static constexpr int kAccStride = 32;  // padded row of the per-block partial-sum matrix
 
 struct GnState {
@@ -147,6 +149,8 @@ struct GnState {
     double g[6];
     double dx[6];
     double sum_res;
+    double cand_total;  // map records scanned, summed over the executed iterations (roofline accounting)
+    double hits_total;  // table probes that hit, summed over the executed iterations
     long long n_valid;
     int iter;       // iterations executed so far
     int done;       // loop finished (converged / failed / cap reached)

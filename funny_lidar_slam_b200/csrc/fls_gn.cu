@@ -25,6 +25,7 @@ __global__ void gn_init_kernel(GnState* s, double t00, double t10, double t20, d
     for (int i = 0; i < 36; ++i) s->H[i] = 0;
     for (int i = 0; i < 6; ++i) s->g[i] = s->dx[i] = 0;
     s->sum_res = 0;
+    s->cand_total = s->hits_total = 0;
     s->n_valid = 0;
     s->iter = 0;
     s->done = 0;
@@ -49,12 +50,14 @@ __global__ void __launch_bounds__(32) gn_solve_kernel(GnState* s, const double* 
     for (int r = 0; r < 6; ++r)
         for (int c = r; c < 6; ++c) H[r * 6 + c] = H[c * 6 + r] = tot[tri6(r, c)];
     for (int a = 0; a < 6; ++a) g[a] = tot[21 + a];
-    const long long n_valid = (long long)(tot[27] + 0.5);
-    const double sum_res = tot[28];
+    const long long n_valid = (long long)(tot[kAccValid] + 0.5);
+    const double sum_res = tot[kAccRes];
     for (int i = 0; i < 36; ++i) s->H[i] = H[i];
     for (int i = 0; i < 6; ++i) s->g[i] = g[i];
     s->n_valid = n_valid;
     s->sum_res = sum_res;
+    s->cand_total += tot[kAccCand];
+    s->hits_total += tot[kAccHits];
     const int it = s->iter;
     s->iter = it + 1;
     for (int i = 0; i < 9; ++i) s->Rprev[i] = s->R[i];

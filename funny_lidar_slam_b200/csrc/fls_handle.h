@@ -31,6 +31,10 @@ struct Handle {
     std::vector<fls_iter_log> h_log;
     int log_cap = 0, log_n = 0;
     double T_final[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    std::vector<cudaEvent_t> prof_ev;  // FLS_FLAG_PROFILE: 2 events per iteration around the residual kernel
+    bool profile = false;
+    long long per_point_iter_bytes = 0;  // fixed part of the algorithmic bytes per point-iteration (set by match_*)
+    long long per_cand_bytes = 0;        // bytes per scanned map record
 
     // maps
     IvoxMap ivox;

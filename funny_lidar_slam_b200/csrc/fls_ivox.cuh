@@ -51,14 +51,18 @@ struct Knn5 {
 // IVoxMap::GetClosestPoint(pt, out, 5, max_range) (ivox_map.cpp:6-37 + voxel_grid_node.cpp:23-42 upstream).
 // Per-voxel top-K followed by a global top-K equals the global top-K of all in-range candidates, which is
 // what is kept here; the nearest ends in slot 0 (the only ordering upstream guarantees).
-__device__ __forceinline__ void ivox_knn5(const IvoxView& m, float qx, float qy, float qz, Knn5& nn) {
+__device__ __forceinline__ void ivox_knn5(const IvoxView& m, float qx, float qy, float qz, Knn5& nn, unsigned& n_cand, unsigned& n_hits) {
     nn.init();
+    n_cand = 0;
+    n_hits = 0;
     const int kx = ivox_coord(qx, m.inv_res), ky = ivox_coord(qy, m.inv_res), kz = ivox_coord(qz, m.inv_res);
 #pragma unroll 1
     for (int s = 0; s < m.n_stencil; ++s) {
         const unsigned long long key = pack_key(kx + c_stencil[s][0], ky + c_stencil[s][1], kz + c_stencil[s][2]);
         unsigned start, count;
         if (!table_find(m.tab, m.mask, key, start, count)) continue;
+        n_cand += count;
+        n_hits += 1;
 #pragma unroll 1
         for (unsigned j = start; j < start + count; ++j) {
             const float4 p = __ldg(m.pts + j);

@@ -118,13 +118,13 @@ __device__ __forceinline__ void plane_lstsq(double (&A)[5][3], double (&c)[3]) {
 
 // Geometry of one source point against the map: returns true when the point produces a valid residual.
 __device__ __forceinline__ bool p2plane_point(const IvoxView& map, const float4 sp, const double* __restrict__ pose /*R[9], t[3]*/,
-                                              double plane_thres, double (&J)[6], double& ad) {
+                                              double plane_thres, double (&J)[6], double& ad, unsigned& n_cand, unsigned& n_hits) {
     const double px = sp.x, py = sp.y, pz = sp.z;
     const float qx = xform_row_d(pose[0], pose[1], pose[2], pose[9], px, py, pz);
     const float qy = xform_row_d(pose[3], pose[4], pose[5], pose[10], px, py, pz);
     const float qz = xform_row_d(pose[6], pose[7], pose[8], pose[11], px, py, pz);
     Knn5 nn;
-    ivox_knn5(map, qx, qy, qz, nn);
+    ivox_knn5(map, qx, qy, qz, nn, n_cand, n_hits);
     if (nn.j4 == 0xffffffffu) return false;  // fewer than 5 neighbours (:271-273)
     double A[5][3];
     {
@@ -183,7 +183,10 @@ __global__ void __launch_bounds__(BLOCK) p2plane_iter_kernel(P2PlaneArgs a) {
     if (i < a.n) {
         const float4 sp = a.src[i];
         double J[6], ad = 0;
-        bool use = p2plane_point(a.map, sp, s_pose, a.plane_thres, J, ad);
+        unsigned n_cand, n_hits;
+        bool use = p2plane_point(a.map, sp, s_pose, a.plane_thres, J, ad, n_cand, n_hits);
+        acc[kAccCand] = (double)n_cand;
+        acc[kAccHits] = (double)n_hits;
         if (use) {
             a.rec0[i] = make_float4((float)J[0], (float)J[1], (float)J[2], (float)J[3]);
             a.rec1[i] = make_float4((float)J[4], (float)J[5], (float)ad, 1.0f);
@@ -202,8 +205,8 @@ __global__ void __launch_bounds__(BLOCK) p2plane_iter_kernel(P2PlaneArgs a) {
                 for (int c = r; c < 6; ++c) acc[k++] += J[r] * J[c];
 #pragma unroll
             for (int r = 0; r < 6; ++r) acc[21 + r] += -J[r] * ad;
-            acc[27] += 1.0;
-            acc[28] += ad;
+            acc[kAccValid] += 1.0;
+            acc[kAccRes] += ad;
         }
     }
     block_reduce_store<BLOCK>(acc, a.partials + (size_t)blockIdx.x * kAccStride);
@@ -214,7 +217,8 @@ __global__ void ivox_knn_test_kernel(IvoxView map, const float4* __restrict__ q,
     if (i >= n) return;
     const float4 p = q[i];
     Knn5 nn;
-    ivox_knn5(map, p.x, p.y, p.z, nn);
+    unsigned nc, nh;
+    ivox_knn5(map, p.x, p.y, p.z, nn, nc, nh);
     const unsigned js[5] = {nn.j0, nn.j1, nn.j2, nn.j3, nn.j4};
     int f = 0;
     for (int k = 0; k < 5; ++k) {

@@ -268,36 +268,51 @@ def make_map_from_scans(world: World, poses, sensor="hdl64", leaf: float = 0.3, 
 
 def make_surface_map(world: World, spacing: float = 0.3, seed: int = 4321, noise: float = 0.02, max_points: int | None = None) -> np.ndarray:
     """Directly sample every surface of the world on a jittered grid (a voxel-filtered prior map without
-    ray casting).  Used for the multi-million-point iVox map of BASELINE config 4."""
+    ray casting).  Used for the multi-million-point iVox map of BASELINE config 4.  Written to touch little
+    fresh memory: one float32 output array filled strip by strip."""
     rng = np.random.default_rng(seed)
     H = world.half
-    parts = []
-
-    def plane(u0, u1, v0, v1, f):
-        nu = max(1, int(round((u1 - u0) / spacing)))
-        nv = max(1, int(round((v1 - v0) / spacing)))
-        uu, vv = np.meshgrid(u0 + (np.arange(nu) + 0.5) * (u1 - u0) / nu, v0 + (np.arange(nv) + 0.5) * (v1 - v0) / nv, indexing="ij")
-        uu = uu.ravel() + rng.uniform(-0.5, 0.5, uu.size) * spacing * 0.9
-        vv = vv.ravel() + rng.uniform(-0.5, 0.5, vv.size) * spacing * 0.9
-        parts.append(f(uu, vv, rng.normal(0, noise, uu.size)))
-
-    plane(-H, H, -H, H, lambda u, v, e: np.stack([u, v, e], 1))
+    # surfaces as (u0, u1, v0, v1, kind, params)
+    surf = [(-H, H, -H, H, "z", (0.0,))]
     for sgn in (-1.0, 1.0):
-        plane(-H, H, 0, world.wall_h, lambda u, v, e, s=sgn: np.stack([s * H + e, u, v], 1))
-        plane(-H, H, 0, world.wall_h, lambda u, v, e, s=sgn: np.stack([u, s * H + e, v], 1))
+        surf.append((-H, H, 0, world.wall_h, "x", (sgn * H,)))
+        surf.append((-H, H, 0, world.wall_h, "y", (sgn * H,)))
     for cx, cy, cz, hx, hy, hz in world.boxes:
-        plane(cx - hx, cx + hx, cy - hy, cy + hy, lambda u, v, e, z=cz + hz: np.stack([u, v, z + e], 1))
+        surf.append((cx - hx, cx + hx, cy - hy, cy + hy, "z", (cz + hz,)))
         for s in (-1.0, 1.0):
-            plane(cy - hy, cy + hy, cz - hz, cz + hz, lambda u, v, e, x=cx + s * hx: np.stack([x + e, u, v], 1))
-            plane(cx - hx, cx + hx, cz - hz, cz + hz, lambda u, v, e, y=cy + s * hy: np.stack([u, y + e, v], 1))
+            surf.append((cy - hy, cy + hy, cz - hz, cz + hz, "x", (cx + s * hx,)))
+            surf.append((cx - hx, cx + hx, cz - hz, cz + hz, "y", (cy + s * hy,)))
     for cx, cy, r, h in world.cyls:
-        plane(0, 2 * np.pi * r, 0, h, lambda u, v, e, cx=cx, cy=cy, r=r: np.stack([cx + (r + e) * np.cos(u / r), cy + (r + e) * np.sin(u / r), v], 1))
-    pts = np.concatenate(parts, 0)
-    pts = pts[pts[:, 2] > -0.5]
-    if max_points is not None and len(pts) > max_points:
-        pts = pts[rng.permutation(len(pts))[:max_points]]
-    inten = np.full((len(pts), 1), 20.0)
-    return np.ascontiguousarray(np.concatenate([pts, inten], 1).astype(np.float32))
+        surf.append((0.0, 2 * np.pi * r, 0.0, h, "c", (cx, cy, r)))
+    dims = [(max(1, int(round((u1 - u0) / spacing))), max(1, int(round((v1 - v0) / spacing)))) for u0, u1, v0, v1, _, _ in surf]
+    total = sum(a * b for a, b in dims)
+    out = np.empty((total, 4), np.float32)
+    out[:, 3] = 20.0
+    pos = 0
+    strip = 1 << 20
+    for (u0, u1, v0, v1, kind, prm), (nu, nv) in zip(surf, dims):
+        m = nu * nv
+        du, dv = (u1 - u0) / nu, (v1 - v0) / nv
+        for s0 in range(0, m, strip):
+            k = np.arange(s0, min(m, s0 + strip))
+            uu = (u0 + ((k // nv) + 0.5) * du + rng.uniform(-0.45, 0.45, k.size) * spacing).astype(np.float32)
+            vv = (v0 + ((k % nv) + 0.5) * dv + rng.uniform(-0.45, 0.45, k.size) * spacing).astype(np.float32)
+            ee = rng.normal(0, noise, k.size).astype(np.float32)
+            o = out[pos + s0: pos + s0 + k.size]
+            if kind == "z":
+                o[:, 0], o[:, 1], o[:, 2] = uu, vv, prm[0] + ee
+            elif kind == "x":
+                o[:, 0], o[:, 1], o[:, 2] = prm[0] + ee, uu, vv
+            elif kind == "y":
+                o[:, 0], o[:, 1], o[:, 2] = uu, prm[0] + ee, vv
+            else:
+                cx, cy, r = prm
+                ang = uu / np.float32(r)
+                o[:, 0], o[:, 1], o[:, 2] = cx + (r + ee) * np.cos(ang), cy + (r + ee) * np.sin(ang), vv
+        pos += m
+    if max_points is not None and len(out) > max_points:
+        out = out[np.sort(rng.permutation(len(out))[:max_points])]
+    return out
 
 
 def make_projected_scan(world: World, pose: np.ndarray, kind: str = "livox", seed: int = 3, lines: int = 6, samples: int = 40000,

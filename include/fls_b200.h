@@ -114,6 +114,7 @@ typedef struct {
 } fls_config;
 
 #define FLS_FLAG_ITER_LOG 1u /* keep per-iteration H, g, dx, n_valid, sum_res for fls_get_iter_log */
+#define FLS_FLAG_PROFILE 2u  /* bracket every residual-kernel launch with CUDA events (fills kernel_ms / kernel_launches) */
 
 typedef struct {
     int32_t iterations;   /* GN iterations executed */
@@ -125,6 +126,9 @@ typedef struct {
     int32_t gpu_launches; /* kernels of this library launched by the call */
     int64_t h2d_bytes;    /* bytes copied host->device by the call */
     int64_t d2h_bytes;    /* bytes copied device->host by the call */
+    float kernel_ms;      /* FLS_FLAG_PROFILE: summed device time of the residual kernel over the executed iterations */
+    int32_t kernel_launches; /* FLS_FLAG_PROFILE: how many launches kernel_ms covers (= iterations) */
+    int64_t algo_bytes;   /* FLS_FLAG_PROFILE: algorithmic bytes those launches moved (DESIGN.md "roofline accounting") */
 } fls_match_stats;
 
 typedef struct {

@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    from funny_lidar_slam_b200._mem import tune_malloc
+    tune_malloc()
     config.addinivalue_line("markers", "gpu: needs a real B200 (run under gpurun / by the driver at round end)")
 
 
