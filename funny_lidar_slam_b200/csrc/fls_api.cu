@@ -1,9 +1,9 @@
 // fls_api.cu — the C ABI of include/fls_b200.h: handle lifetime, host<->device staging and the host side of
 // each plug-in's Match / AddCloudToLocalMap / GetFitnessScore.  The Gauss-Newton loop itself runs on the
 // device (residual kernel + gn_solve kernel per iteration, convergence decided on the device); the host
-// enqueues the iteration cap and reads the 1 KB state block back once.
+// enqueues the iteration cap and reads the ~1 KB state block back once.
+#include <cmath>
 #include <cstring>
-#include <mutex>
 #include <new>
 #include <vector>
 
@@ -14,6 +14,7 @@ namespace fls {
 
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& s) { g_last_error = s; }
+const char* last_error_cstr() { return g_last_error.c_str(); }
 
 Handle::Handle(const fls_config& c) : cfg(c) {
     FLS_CUDA(cudaSetDevice(cfg.device));
@@ -22,7 +23,14 @@ Handle::Handle(const fls_config& c) : cfg(c) {
     FLS_CUDA(cudaEventCreate(&ev1));
     FLS_CUDA(cudaMallocHost(&h_state, sizeof(GnState)));
     state.reserve(1);
+    fit_out.reserve(2);
     ivox.set_resolution(cfg.ivox_resolution);
+    ivox.key_mode = 0;
+    ndt.configure(cfg.ndt_voxel_size, cfg.ndt_min_points_in_voxel, cfg.ndt_max_points_in_voxel, cfg.ndt_capacity);
+    // search grid of the bounded exact 1-NN: cell >= sqrt(max_correspond_distance)  [quirk 4]
+    icp_grid.key_mode = 1;
+    icp_grid.set_resolution((float)(std::sqrt(cfg.icp_max_correspond_distance > 0 ? cfg.icp_max_correspond_distance : 1.0) * 1.001));
+    fit_grid.key_mode = 1;
     profile = (cfg.flags & FLS_FLAG_PROFILE) != 0;
     if (profile) {
         prof_ev.resize(2 * (size_t)(cfg.max_iterations > 0 ? cfg.max_iterations : 1));
@@ -62,17 +70,18 @@ const float4* Handle::upload(const void* pts, size_t n, size_t stride, DevBuf<fl
     return dst.p;
 }
 
-IvoxView Handle::ivox_view() const {
+IvoxView Handle::grid_view(const IvoxMap& g) const {
     IvoxView v;
-    v.pts = ivox.pts_sorted.p;
-    v.tab = ivox.table.p;
-    v.mask = ivox.mask;
-    v.inv_res = ivox.inv_res;
+    v.pts = g.pts_sorted.p;
+    v.tab = g.table.p;
+    v.mask = g.mask;
+    v.inv_res = g.inv_res;
     v.max_range2 = cfg.ivox_max_range * cfg.ivox_max_range;
     static const int counts[4] = {1, 7, 19, 27};
     v.n_stencil = counts[cfg.ivox_nearby];
     return v;
 }
+IvoxView Handle::ivox_view() const { return grid_view(ivox); }
 
 void Handle::begin_call() {
     FLS_CUDA(cudaSetDevice(cfg.device));
@@ -95,6 +104,32 @@ void Handle::end_call(fls_match_stats* st) {
     }
 }
 
+void Handle::set_fit_cloud(const float4* d, size_t n) {
+    fit_cloud.reserve(n);
+    if (n) FLS_CUDA(cudaMemcpyAsync(fit_cloud.p, d, n * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+    fit_cloud_n = n;
+    fit_cloud_version++;
+}
+
+// ---- generic device-resident GN loop ---------------------------------------------------------------------------
+template <typename Launch>
+static void gn_loop(Handle& h, int method, int grid, int min_effective, Launch&& launch_residual) {
+    GnParams gp;
+    gp.method = method;
+    gp.max_iterations = h.cfg.max_iterations;
+    gp.min_effective = min_effective;
+    gp.n_blocks = grid;
+    gp.rot_thres = h.cfg.rotation_converge_thres;
+    gp.pos_thres = h.cfg.position_converge_thres;
+    for (int it = 0; it < h.cfg.max_iterations; ++it) {
+        if (h.profile) FLS_CUDA(cudaEventRecord(h.prof_ev[2 * it], h.stream));
+        launch_residual();
+        if (h.profile) FLS_CUDA(cudaEventRecord(h.prof_ev[2 * it + 1], h.stream));
+        launch_gn_solve(h.state.p, h.partials.p, gp, h.log.p, h.log_cap, h.stream);
+        h.launches += (grid > 0 ? 2 : 1);
+    }
+}
+
 // ---- LoamPointToPlaneIVOX ------------------------------------------------------------------------------------
 int Handle::add_cloud_ivox(const void* pts, size_t n, size_t stride) {
     if (cfg.localization_mode) ivox.clear();  // loam_point_to_plane_ivox.h:64-69 upstream: map re-created per call
@@ -103,6 +138,7 @@ int Handle::add_cloud_ivox(const void* pts, size_t n, size_t stride) {
     const int rc = ivox.append_and_build(d, n, cfg.ivox_capacity, stream);
     launches += ivox.launches;
     ivox.launches = 0;
+    if (cfg.localization_mode) set_fit_cloud(d, n);  // :134-138 kd-tree over the raw planar cloud
     return rc;
 }
 
@@ -127,25 +163,196 @@ int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* co
     a.rec1 = rec1.p;
     a.flags = flags.p;
     a.partials = partials.p;
-    GnParams gp;
-    gp.method = FLS_P2PLANE_IVOX;
-    gp.max_iterations = cfg.max_iterations;
-    gp.min_effective = 50;
-    gp.n_blocks = grid;
-    gp.rot_thres = cfg.rotation_converge_thres;
-    gp.pos_thres = cfg.position_converge_thres;
     // roofline accounting: 16 B source point + n_stencil x 16 B slot probes + 32 B persistent
     // record per point-iteration, 16 B per map record resident in the hit voxels.
     per_point_iter_bytes = 16 + 16LL * a.map.n_stencil + 32;
     per_cand_bytes = 16;
-    for (int it = 0; it < cfg.max_iterations; ++it) {
-        if (profile) FLS_CUDA(cudaEventRecord(prof_ev[2 * it], stream));
-        launch_p2plane_iter(a, stream);
-        if (profile) FLS_CUDA(cudaEventRecord(prof_ev[2 * it + 1], stream));
-        launch_gn_solve(state.p, partials.p, gp, log.p, log_cap, stream);
-        launches += (ni > 0 ? 2 : 1);
-    }
+    per_hit_bytes = 0;
+    gn_loop(*this, FLS_P2PLANE_IVOX, grid, 50, [&] { launch_p2plane_iter(a, stream); });
+    last_src = d_src;
+    last_src_n = n;
     return finish_match(T, converged, st, (long long)n);
+}
+
+// ---- IncrementalNDT ----------------------------------------------------------------------------------------------
+int Handle::add_cloud_ndt(const float4* d_cloud, size_t n) {
+    const int rc = ndt.add_cloud(d_cloud, n, cfg.source_cloud_filter_size, ndt_first_scan, stream);
+    launches += ndt.launches;
+    ndt.launches = 0;
+    if (cfg.localization_mode && rc == FLS_OK) {
+        // kdtree_flann_.setInputCloud(cloud_world) — the voxel-filtered cloud (incremental_ndt.h:188-190)
+        const size_t nf = voxel_grid_device(d_cloud, n, cfg.source_cloud_filter_size, ndt.filtered.p, ndt.scratch, stream, &launches);
+        set_fit_cloud(ndt.filtered.p, nf);
+    }
+    ndt_first_scan = cfg.localization_mode != 0;  // :222-226
+    return rc;
+}
+
+int Handle::match_ndt(const float4* d_in, size_t n_in, double* T, int* converged, fls_match_stats* st) {
+    if (ndt.n_vox == 0) return FLS_ERR_NO_MAP;  // CHECK(!grids_.empty())
+    src_f.reserve(n_in);
+    const size_t n = voxel_grid_device(d_in, n_in, cfg.source_cloud_filter_size, src_f.p, scratch, stream, &launches);  // :232
+    const int ni = (int)n;
+    const int grid = ndt_grid(ni);
+    partials.reserve((size_t)(grid > 0 ? grid : 1) * kAccStride);
+    double T_in[16];
+    std::memcpy(T_in, T, sizeof(T_in));
+    launch_gn_init(state.p, T, stream);
+    launches++;
+    NdtArgs a;
+    a.src = src_f.p;
+    a.n = ni;
+    a.map = ndt.view();
+    a.outlier_thres = cfg.ndt_outlier_thres;
+    a.state = state.p;
+    a.partials = partials.p;
+    // roofline accounting: 16 B source point + 7 x 16 B slot probes per point-iteration,
+    // 80 B voxel record per estimated voxel hit; the 6x6 sums are fused (no per-point output).
+    per_point_iter_bytes = 16 + 16LL * 7;
+    per_cand_bytes = 80;
+    per_hit_bytes = 0;
+    gn_loop(*this, FLS_NDT, grid, cfg.ndt_min_effective_pts, [&] { launch_ndt_iter(a, stream); });
+    last_src = src_f.p;
+    last_src_n = n;
+    const int rc = finish_match(T, converged, st, (long long)n);
+    if (rc != FLS_OK) return rc;
+    if (!h_state->failed && !cfg.localization_mode) {
+        // :326-330 — the scan enters the map transformed by the INPUT guess T, not the optimised pose  [quirk 6]
+        stage2.reserve(n);
+        launch_transform_f(src_f.p, n, T_in, stage2.p, stream);
+        launches++;
+        const int rc2 = add_cloud_ndt(stage2.p, n);
+        FLS_CUDA(cudaStreamSynchronize(stream));
+        if (st) st->gpu_launches = launches;
+        if (rc2 != FLS_OK) return rc2;
+    }
+    return FLS_OK;
+}
+
+// ---- IcpOptimized ------------------------------------------------------------------------------------------------
+int Handle::add_cloud_icp(const float4* d_cloud, size_t n) {
+    const float4* merged = d_cloud;
+    size_t n_merged = n;
+    if (!cfg.localization_mode) {  // icp_optimized.h:173-185 sliding window of the last local_map_size clouds
+        std::unique_ptr<Cloud> c(new Cloud());
+        c->buf.reserve(n);
+        if (n) FLS_CUDA(cudaMemcpyAsync(c->buf.p, d_cloud, n * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        c->n = n;
+        icp_deque.push_back(std::move(c));
+        if ((long long)icp_deque.size() > (long long)cfg.local_map_size) {
+            FLS_CUDA(cudaStreamSynchronize(stream));
+            icp_deque.pop_front();
+        }
+        n_merged = 0;
+        for (auto& q : icp_deque) n_merged += q->n;
+        stage2.reserve(n_merged);
+        size_t off = 0;
+        for (auto& q : icp_deque) {
+            if (q->n) FLS_CUDA(cudaMemcpyAsync(stage2.p + off, q->buf.p, q->n * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+            off += q->n;
+        }
+        merged = stage2.p;
+    }
+    // local_map_ptr_ = VoxelGridCloud(local_map_ptr_, map_cloud_filter_size_)  (:187)
+    fit_cloud.reserve(n_merged);
+    const size_t nm = voxel_grid_device(merged, n_merged, cfg.map_cloud_filter_size, fit_cloud.p, scratch, stream, &launches);
+    fit_cloud_n = nm;
+    fit_cloud_version++;
+    icp_grid.clear();
+    const int rc = icp_grid.append_and_build(fit_cloud.p, nm, 0, stream);
+    launches += icp_grid.launches;
+    icp_grid.launches = 0;
+    return rc;
+}
+
+static void mat3_from_T(const double* T, double* R) {
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) R[r * 3 + c] = T[c * 4 + r];
+}
+
+int Handle::match_icp(const float4* d_in, size_t n_in, double* T, int* converged, fls_match_stats* st) {
+    if (n_in <= 10) return FLS_ERR_TOO_FEW_POINTS;  // CHECK_GT(ordered_cloud_.size(), 10u)  (:55)
+    if (icp_grid.n_pts == 0) return FLS_ERR_NO_MAP;
+    src_f.reserve(n_in);
+    const size_t n = voxel_grid_device(d_in, n_in, cfg.source_cloud_filter_size, src_f.p, scratch, stream, &launches);  // :57
+    const int ni = (int)n;
+    const int grid = icp_grid_blocks(ni);
+    partials.reserve((size_t)(grid > 0 ? grid : 1) * kAccStride);
+    launch_gn_init(state.p, T, stream);
+    launches++;
+    IcpArgs a;
+    a.src = src_f.p;
+    a.n = ni;
+    a.map = grid_view(icp_grid);
+    a.max_corr = cfg.icp_max_correspond_distance;
+    a.state = state.p;
+    a.partials = partials.p;
+    // roofline accounting: 16 B source point + 27 x 16 B slot probes, 16 B per scanned map record
+    per_point_iter_bytes = 16 + 16LL * 27;
+    per_cand_bytes = 16;
+    per_hit_bytes = 0;
+    gn_loop(*this, FLS_ICP_P2P, grid, 0, [&] { launch_icp_iter(a, stream); });
+    last_src = src_f.p;
+    last_src_n = n;
+    const int rc = finish_match(T, converged, st, (long long)n);
+    if (rc != FLS_OK) return rc;
+    if (h_state->converged && !cfg.localization_mode) {
+        // IsNeedAddCloud (:218-236): key-frame gating on translation / RPY deltas against a persistent last_T
+        if (!icp_have_last) {
+            std::memcpy(icp_last_T, T, sizeof(icp_last_T));
+            icp_have_last = true;
+        }
+        double Rl[9], Rc[9], Rli[9], Rd[9];
+        mat3_from_T(icp_last_T, Rl);
+        mat3_from_T(T, Rc);
+        {  // 3x3 inverse by cofactors
+            const double c00 = Rl[4] * Rl[8] - Rl[5] * Rl[7], c01 = Rl[5] * Rl[6] - Rl[3] * Rl[8], c02 = Rl[3] * Rl[7] - Rl[4] * Rl[6];
+            const double id = 1.0 / (Rl[0] * c00 + Rl[1] * c01 + Rl[2] * c02);
+            Rli[0] = c00 * id; Rli[1] = (Rl[2] * Rl[7] - Rl[1] * Rl[8]) * id; Rli[2] = (Rl[1] * Rl[5] - Rl[2] * Rl[4]) * id;
+            Rli[3] = c01 * id; Rli[4] = (Rl[0] * Rl[8] - Rl[2] * Rl[6]) * id; Rli[5] = (Rl[2] * Rl[3] - Rl[0] * Rl[5]) * id;
+            Rli[6] = c02 * id; Rli[7] = (Rl[1] * Rl[6] - Rl[0] * Rl[7]) * id; Rli[8] = (Rl[0] * Rl[4] - Rl[1] * Rl[3]) * id;
+        }
+        mat3_mul(Rli, Rc, Rd);
+        const double roll = std::atan2(Rd[7], Rd[8]), pitch = std::asin(-Rd[6]), yaw = std::atan2(Rd[3], Rd[0]);
+        const double dt[3] = {T[12] - icp_last_T[12], T[13] - icp_last_T[13], T[14] - icp_last_T[14]};
+        if (norm3(dt) > cfg.dist_thre_add_cloud || std::fabs(roll) > cfg.rot_thre_add_cloud || std::fabs(pitch) > cfg.rot_thre_add_cloud ||
+            std::fabs(yaw) > cfg.rot_thre_add_cloud) {
+            std::memcpy(icp_last_T, T, sizeof(icp_last_T));
+            stage.reserve(n);
+            launch_transform_f(src_f.p, n, T, stage.p, stream);  // :156 TransformPointCloud(source, final) in float
+            launches++;
+            const int rc2 = add_cloud_icp(stage.p, n);
+            FLS_CUDA(cudaStreamSynchronize(stream));
+            if (st) st->gpu_launches = launches;
+            if (rc2 != FLS_OK) return rc2;
+        }
+    }
+    return FLS_OK;
+}
+
+// ---- GetFitnessScore -------------------------------------------------------------------------------------------------
+int Handle::fitness(float max_range, float* score) {
+    *score = 3.402823466e+38f;  // FloatNaN / "no inliers" upstream
+    if (cfg.method != FLS_ICP_P2P && !cfg.localization_mode) return FLS_OK;  // FloatNaN outside localization mode
+    if (fit_cloud_n == 0 || last_src == nullptr || last_src_n == 0 || !(max_range > 0.f)) return FLS_OK;
+    begin_call();
+    if (fit_grid_version != fit_cloud_version || fit_grid_range != max_range) {
+        fit_grid.set_resolution(std::sqrt(max_range) * 1.001f);
+        fit_grid.clear();
+        const int rc = fit_grid.append_and_build(fit_cloud.p, fit_cloud_n, 0, stream);
+        launches += fit_grid.launches;
+        fit_grid.launches = 0;
+        if (rc != FLS_OK) return rc;
+        fit_grid_version = fit_cloud_version;
+        fit_grid_range = max_range;
+    }
+    launch_fitness(grid_view(fit_grid), last_src, (int)last_src_n, T_final, max_range, fit_out.p, stream);
+    launches++;
+    double h[2] = {0, 0};
+    FLS_CUDA(cudaMemcpyAsync(h, fit_out.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    end_call(nullptr);
+    if (h[1] > 0) *score = (float)(h[0] / h[1]);
+    return FLS_OK;
 }
 
 // read the device state back, fill T / stats / iteration log
@@ -182,7 +389,8 @@ int Handle::finish_match(double* T, int* converged, fls_match_stats* st, long lo
             }
             st->kernel_ms = tot;
             st->kernel_launches = s.iter;
-            st->algo_bytes = (long long)s.iter * n_source * per_point_iter_bytes + (long long)(s.cand_total + 0.5) * per_cand_bytes;
+            st->algo_bytes = (long long)s.iter * n_source * per_point_iter_bytes + (long long)(s.cand_total + 0.5) * per_cand_bytes +
+                             (long long)(s.hits_total + 0.5) * per_hit_bytes;
         }
     }
     return FLS_OK;
@@ -202,6 +410,8 @@ using fls::Handle;
         return FLS_ERR_CUDA;                                   \
     }
 
+static bool stride_ok(size_t stride) { return stride == 16 || (stride >= 20 && stride % 4 == 0); }
+
 extern "C" {
 
 int fls_abi_version(void) { return FLS_ABI_VERSION; }
@@ -212,7 +422,7 @@ int fls_device_count(void) {
     return n;
 }
 
-const char* fls_last_error(void) { return fls::g_last_error.c_str(); }
+const char* fls_last_error(void) { return fls::last_error_cstr(); }
 
 const char* fls_strerror(int status) {
     switch (status) {
@@ -291,6 +501,16 @@ static int validate(const fls_config* c) {
     if (c->method == FLS_P2PLANE_IVOX) {
         if (!(c->point_to_planar_thres < 1e300) || !(c->ivox_resolution > 0.f)) return FLS_ERR_INVALID_ARG;
         if (c->ivox_k != 5) return FLS_ERR_UNSUPPORTED;  // upstream always asks for 5 (loam_point_to_plane_ivox.h:269)
+    } else if (c->method == FLS_NDT) {
+        if (!(c->ndt_voxel_size > 0) || !(c->ndt_voxel_size < 1e300) || !(c->ndt_outlier_thres < 1e300) || !(c->source_cloud_filter_size > 0.f) ||
+            c->ndt_capacity <= 0 || c->ndt_capacity == 2147483647 || c->ndt_min_points_in_voxel < 0 || c->ndt_min_points_in_voxel > 64)
+            return FLS_ERR_INVALID_ARG;
+    } else if (c->method == FLS_ICP_P2P) {
+        if (!(c->icp_max_correspond_distance > 0) || !(c->icp_max_correspond_distance < 1e300) || !(c->source_cloud_filter_size > 0.f) ||
+            !(c->map_cloud_filter_size > 0.f) || c->local_map_size <= 0)
+            return FLS_ERR_INVALID_ARG;
+    } else {
+        return FLS_ERR_UNSUPPORTED;  // PointToPlane_KdTree / LoamFull_KdTree: SURVEY.md §8f row 3, not built yet
     }
     return FLS_OK;
 }
@@ -316,15 +536,16 @@ void fls_destroy(fls_handle* h) { delete reinterpret_cast<Handle*>(h); }
 
 int fls_add_cloud(fls_handle* hh, int n_clouds, const void* const* pts, const size_t* n, size_t stride) {
     Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h || !pts || !n || n_clouds < 1 || (stride != 16 && (stride < 20 || stride % 4))) return FLS_ERR_INVALID_ARG;
+    if (!h || !pts || !n || n_clouds < 1 || !stride_ok(stride)) return FLS_ERR_INVALID_ARG;
+    if (n_clouds != 1) return FLS_ERR_INVALID_ARG;  // CHECK_EQ(cloud_list.size(), 1) in all three built plug-ins
+    if (!pts[0] && n[0]) return FLS_ERR_INVALID_ARG;
     FLS_TRY
     h->begin_call();
     int rc = FLS_ERR_UNSUPPORTED;
     switch (h->cfg.method) {
-        case FLS_P2PLANE_IVOX:
-            if (n_clouds != 1) return FLS_ERR_INVALID_ARG;  // CHECK_EQ(cloud_list.size(), 1)
-            rc = h->add_cloud_ivox(pts[0], n[0], stride);
-            break;
+        case FLS_P2PLANE_IVOX: rc = h->add_cloud_ivox(pts[0], n[0], stride); break;
+        case FLS_NDT: rc = h->add_cloud_ndt(h->upload(pts[0], n[0], stride, h->stage), n[0]); break;
+        case FLS_ICP_P2P: rc = h->add_cloud_icp(h->upload(pts[0], n[0], stride, h->stage), n[0]); break;
         default: break;
     }
     h->end_call(nullptr);
@@ -336,6 +557,8 @@ static int match_dispatch(Handle* h, const float4* d_ordered, size_t n_ordered, 
                           int* converged, fls_match_stats* st) {
     switch (h->cfg.method) {
         case FLS_P2PLANE_IVOX: return h->match_p2plane_ivox(d_planar, n_planar, T, converged, st);
+        case FLS_NDT: return h->match_ndt(d_ordered, n_ordered, T, converged, st);
+        case FLS_ICP_P2P: return h->match_icp(d_ordered, n_ordered, T, converged, st);
         default: return FLS_ERR_UNSUPPORTED;
     }
 }
@@ -343,7 +566,7 @@ static int match_dispatch(Handle* h, const float4* d_ordered, size_t n_ordered, 
 int fls_match(fls_handle* hh, const void* ordered, size_t n_ordered, const void* planar, size_t n_planar, const void* corner, size_t n_corner,
               size_t stride, double T[16], int* converged, fls_match_stats* st) {
     Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h || !T || (stride != 16 && (stride < 20 || stride % 4))) return FLS_ERR_INVALID_ARG;
+    if (!h || !T || !stride_ok(stride)) return FLS_ERR_INVALID_ARG;
     (void)corner;
     (void)n_corner;
     FLS_TRY
@@ -377,9 +600,9 @@ int fls_match_device(fls_handle* hh, const void* d_points, size_t n, double T[16
 int fls_fitness(fls_handle* hh, float max_range, float* score) {
     Handle* h = reinterpret_cast<Handle*>(hh);
     if (!h || !score) return FLS_ERR_INVALID_ARG;
-    (void)max_range;
-    *score = 3.402823466e+38f;  // FloatNaN upstream (constant_variable.h:11)
-    return FLS_ERR_UNSUPPORTED;
+    FLS_TRY
+    return h->fitness(max_range, score);
+    FLS_CATCH
 }
 
 int fls_get_iter_log(const fls_handle* hh, fls_iter_log* out, int capacity) {
@@ -399,13 +622,22 @@ int fls_get_map_info(const fls_handle* hh, fls_map_info* out) {
         out->n_voxels = (long long)h->ivox.n_vox;
         out->table_slots = h->ivox.n_pts ? (long long)h->ivox.mask + 1 : 0;
         out->bytes = (long long)h->ivox.bytes();
+    } else if (h->cfg.method == FLS_NDT) {
+        out->n_voxels = (long long)h->ndt.n_vox;
+        out->table_slots = (long long)h->ndt.slots;
+        out->bytes = (long long)h->ndt.bytes();
+    } else if (h->cfg.method == FLS_ICP_P2P) {
+        out->n_points = (long long)h->icp_grid.n_pts;
+        out->n_voxels = (long long)h->icp_grid.n_vox;
+        out->table_slots = h->icp_grid.n_pts ? (long long)h->icp_grid.mask + 1 : 0;
+        out->bytes = (long long)h->icp_grid.bytes();
     }
     return FLS_OK;
 }
 
 int fls_ivox_knn(fls_handle* hh, const void* queries, size_t n, size_t stride, int k, float* out_pts, int32_t* out_count) {
     Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h || !queries || !out_pts || !out_count || k != 5) return FLS_ERR_INVALID_ARG;
+    if (!h || !queries || !out_pts || !out_count || k != 5 || !stride_ok(stride)) return FLS_ERR_INVALID_ARG;
     if (h->cfg.method != FLS_P2PLANE_IVOX) return FLS_ERR_UNSUPPORTED;
     if (h->ivox.n_pts == 0) return FLS_ERR_NO_MAP;
     FLS_TRY
@@ -424,8 +656,40 @@ int fls_ivox_knn(fls_handle* hh, const void* queries, size_t n, size_t stride, i
 }
 
 int fls_voxel_grid(int device, const void* pts, size_t n, size_t stride, float leaf, float* out, size_t* n_out) {
-    (void)device; (void)pts; (void)n; (void)stride; (void)leaf; (void)out; (void)n_out;
-    return FLS_ERR_UNSUPPORTED;
+    if ((!pts && n) || !out || !n_out || !stride_ok(stride) || !(leaf > 0.f)) return FLS_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return FLS_ERR_NO_DEVICE;
+    FLS_TRY
+    FLS_CUDA(cudaSetDevice(device));
+    *n_out = 0;
+    if (n == 0) return FLS_OK;
+    cudaStream_t st;
+    FLS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int rc = FLS_OK;
+    try {
+        fls::DevBuf<unsigned char> raw;
+        fls::DevBuf<float4> in, outb;
+        fls::BuildScratch sc;
+        in.reserve(n);
+        outb.reserve(n);
+        if (stride == 16) {
+            FLS_CUDA(cudaMemcpyAsync(in.p, pts, n * 16, cudaMemcpyHostToDevice, st));
+        } else {
+            raw.reserve(n * stride);
+            FLS_CUDA(cudaMemcpyAsync(raw.p, pts, n * stride, cudaMemcpyHostToDevice, st));
+            fls::launch_repack(raw.p, n, stride, in.p, st);
+        }
+        int l = 0;
+        const size_t m = fls::voxel_grid_device(in.p, n, leaf, outb.p, sc, st, &l);
+        FLS_CUDA(cudaMemcpyAsync(out, outb.p, m * 16, cudaMemcpyDeviceToHost, st));
+        FLS_CUDA(cudaStreamSynchronize(st));
+        *n_out = m;
+    } catch (const fls::CudaError& e) {
+        rc = e.status;
+    }
+    cudaStreamDestroy(st);
+    return rc;
+    FLS_CATCH
 }
 
 int fls_extract_features(const fls_feature_cfg* cfg, const float* depth, const int32_t* col, size_t n, const int32_t* row_start,

@@ -1,5 +1,7 @@
 // fls_handle.h — the object behind `fls_handle*`: configuration, stream, device-resident map and scan state.
 #pragma once
+#include <deque>
+#include <memory>
 #include <vector>
 
 #include "fls_common.cuh"
@@ -20,8 +22,10 @@ struct Handle {
 
     // scan-side buffers
     DevBuf<unsigned char> raw;  // strided caller records before repacking
-    DevBuf<float4> src;         // scan entering the GN loop (packed float4)
+    DevBuf<float4> src;         // uploaded scan (packed float4)
+    DevBuf<float4> src_f;       // scan after Match's own VoxelGridCloud (ICP / NDT)
     DevBuf<float4> stage;       // clouds handed to AddCloudToLocalMap
+    DevBuf<float4> stage2;      // transformed / filtered intermediates
     DevBuf<float4> rec0, rec1;  // persistent per-point {J, |d|} records (LOAM plug-ins)
     DevBuf<unsigned char> flags;
     DevBuf<double> partials;
@@ -35,9 +39,33 @@ struct Handle {
     bool profile = false;
     long long per_point_iter_bytes = 0;  // fixed part of the algorithmic bytes per point-iteration (set by match_*)
     long long per_cand_bytes = 0;        // bytes per scanned map record
+    long long per_hit_bytes = 0;         // bytes per table probe that hit (NDT voxel record)
+    BuildScratch scratch;                // voxel-grid passes of Match
+
+    // source cloud of the last Match (for GetFitnessScore): device pointer + count
+    const float4* last_src = nullptr;
+    size_t last_src_n = 0;
 
     // maps
-    IvoxMap ivox;
+    IvoxMap ivox;      // LoamPointToPlaneIVOX
+    NdtMap ndt;        // IncrementalNDT
+    bool ndt_first_scan = true;  // flag_first_scan_ (incremental_ndt.h:394)
+    IvoxMap icp_grid;  // IcpOptimized: floor-keyed search grid over local_map_ptr_
+    struct Cloud {
+        DevBuf<float4> buf;
+        size_t n = 0;
+    };
+    std::deque<std::unique_ptr<Cloud>> icp_deque;  // cloud_deque_ (icp_optimized.h:246)
+    bool icp_have_last = false;                    // `static last_T` of IsNeedAddCloud (:219)  [quirk 7]
+    double icp_last_T[16];
+
+    // GetFitnessScore support: cloud the upstream kd-tree is built on + a search grid sized for max_range
+    DevBuf<float4> fit_cloud;
+    size_t fit_cloud_n = 0;
+    unsigned long long fit_cloud_version = 0, fit_grid_version = ~0ull;
+    float fit_grid_range = -1.f;
+    IvoxMap fit_grid;
+    DevBuf<double> fit_out;
 
     explicit Handle(const fls_config& c);
     ~Handle();
@@ -48,10 +76,20 @@ struct Handle {
     void end_call(fls_match_stats* st);
     const float4* upload(const void* pts, size_t n, size_t stride, DevBuf<float4>& dst);
     IvoxView ivox_view() const;
+    IvoxView grid_view(const IvoxMap& g) const;
     int finish_match(double* T, int* converged, fls_match_stats* st, long long n_source);
+    void set_fit_cloud(const float4* d, size_t n);
 
     int add_cloud_ivox(const void* pts, size_t n, size_t stride);
     int match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st);
+
+    int add_cloud_ndt(const float4* d_cloud, size_t n);
+    int match_ndt(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st);
+
+    int add_cloud_icp(const float4* d_cloud, size_t n);
+    int match_icp(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st);
+
+    int fitness(float max_range, float* score);
 };
 
 }  // namespace fls

@@ -27,6 +27,9 @@ static __device__ __constant__ signed char c_stencil[27][4] = {
 
 // IVoxMap::Pos2Grid (ivox_map.cpp:145-147 upstream): round(p * inv_res), fp32 product, half away from zero
 __device__ __forceinline__ int ivox_coord(float v, float inv_res) { return (int)roundf(__fmul_rn(v, inv_res)); }
+// uniform search grid (bounded exact NN): floor(p * inv_cell)
+__device__ __forceinline__ int floor_coord(float v, float inv_res) { return (int)floorf(__fmul_rn(v, inv_res)); }
+__device__ __forceinline__ int grid_coord(float v, float inv_res, int key_mode) { return key_mode ? floor_coord(v, inv_res) : ivox_coord(v, inv_res); }
 
 struct Knn5 {
     float d0, d1, d2, d3, d4;

@@ -1,11 +1,14 @@
-// fls_kernels.h — launch interfaces of the residual kernels (K1 p2plane/iVox, K2 NDT, K3 ICP).
+// fls_kernels.h — launch interfaces of the residual kernels (K1 p2plane/iVox, K2 NDT, K3 ICP) and GetFitnessScore.
 #pragma once
 #include "fls_common.cuh"
 #include "fls_ivox.cuh"
+#include "fls_maps.h"
 
 namespace fls {
 
 static constexpr int kP2PlaneBlock = 128;
+static constexpr int kNdtBlock = 128;
+static constexpr int kIcpBlock = 128;
 
 struct P2PlaneArgs {
     const float4* __restrict__ src;  // body-frame scan, packed float4
@@ -18,9 +21,33 @@ struct P2PlaneArgs {
     unsigned char* __restrict__ flags;
     double* __restrict__ partials;  // [grid][kAccStride]
 };
-
 int p2plane_grid(int n);
 void launch_p2plane_iter(const P2PlaneArgs& a, cudaStream_t st);
 void launch_ivox_knn_test(const IvoxView& map, const float4* d_q, int n, float4* d_out, int* d_found, cudaStream_t st);
+
+struct NdtArgs {
+    const float4* __restrict__ src;  // voxel-filtered scan, body frame
+    int n;
+    NdtView map;
+    double outlier_thres;
+    GnState* state;
+    double* __restrict__ partials;
+};
+int ndt_grid(int n);
+void launch_ndt_iter(const NdtArgs& a, cudaStream_t st);
+
+struct IcpArgs {
+    const float4* __restrict__ src;  // voxel-filtered scan, body frame
+    int n;
+    IvoxView map;  // floor-keyed search grid over the voxel-filtered local map
+    double max_corr;
+    GnState* state;
+    double* __restrict__ partials;
+};
+int icp_grid_blocks(int n);
+void launch_icp_iter(const IcpArgs& a, cudaStream_t st);
+
+// d_out2[0] = sum of squared NN distances <= max_range, d_out2[1] = how many; T column-major (cast to float inside)
+void launch_fitness(const IvoxView& g, const float4* d_src, int n, const double* T_colmajor, float max_range, double* d_out2, cudaStream_t st);
 
 }  // namespace fls

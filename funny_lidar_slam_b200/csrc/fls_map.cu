@@ -20,12 +20,12 @@ BuildScratch::~BuildScratch() {
 
 namespace {
 
-__global__ void ivox_keys_kernel(const float4* __restrict__ pts, size_t n, float inv_res, unsigned long long* __restrict__ keys,
+__global__ void ivox_keys_kernel(const float4* __restrict__ pts, size_t n, float inv_res, int key_mode, unsigned long long* __restrict__ keys,
                                  unsigned* __restrict__ idx) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = pts[i];
-    keys[i] = morton_key(ivox_coord(p.x, inv_res), ivox_coord(p.y, inv_res), ivox_coord(p.z, inv_res));
+    keys[i] = morton_key(grid_coord(p.x, inv_res, key_mode), grid_coord(p.y, inv_res, key_mode), grid_coord(p.z, inv_res, key_mode));
     idx[i] = (unsigned)i;
 }
 
@@ -45,12 +45,12 @@ __global__ void table_clear_kernel(HashSlot* tab, size_t slots) {
 
 // one thread per voxel run: key recomputed from the run's first point
 __global__ void ivox_insert_kernel(const float4* __restrict__ pts_sorted, const unsigned* __restrict__ starts, const unsigned* __restrict__ counts,
-                                   int n_runs, float inv_res, HashSlot* tab, unsigned mask) {
+                                   int n_runs, float inv_res, int key_mode, HashSlot* tab, unsigned mask) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_runs) return;
     const unsigned s = starts[v];
     const float4 p = pts_sorted[s];
-    const unsigned long long key = pack_key(ivox_coord(p.x, inv_res), ivox_coord(p.y, inv_res), ivox_coord(p.z, inv_res));
+    const unsigned long long key = pack_key(grid_coord(p.x, inv_res, key_mode), grid_coord(p.y, inv_res, key_mode), grid_coord(p.z, inv_res, key_mode));
     unsigned h = hash_key(key) & mask;
     for (;;) {
         const unsigned long long prev = atomicCAS(&tab[h].key, kEmptyKey, key);
@@ -111,7 +111,7 @@ int IvoxMap::append_and_build(const float4* d_new, size_t n_new, long long capac
     sc.num_runs.reserve(1);
     pts_sorted.reserve(n);
 
-    ivox_keys_kernel<<<grid_for(n, 256), 256, 0, st>>>(pts_all.p, n, inv_res, sc.keys.p, sc.idx.p);
+    ivox_keys_kernel<<<grid_for(n, 256), 256, 0, st>>>(pts_all.p, n, inv_res, key_mode, sc.keys.p, sc.idx.p);
     size_t tmp1 = 0, tmp2 = 0, tmp3 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp1, sc.keys.p, sc.keys_sorted.p, sc.idx.p, sc.idx_sorted.p, (int)n, 0, 63, st);
     cub::DeviceRunLengthEncode::Encode(nullptr, tmp2, sc.keys_sorted.p, sc.uniq.p, sc.counts.p, sc.num_runs.p, (int)n, st);
@@ -135,7 +135,7 @@ int IvoxMap::append_and_build(const float4* d_new, size_t n_new, long long capac
     table.reserve(slots);
     mask = (unsigned)(slots - 1);
     table_clear_kernel<<<grid_for(slots, 256), 256, 0, st>>>(table.p, slots);
-    ivox_insert_kernel<<<grid_for(runs, 256), 256, 0, st>>>(pts_sorted.p, sc.starts.p, sc.counts.p, runs, inv_res, table.p, mask);
+    ivox_insert_kernel<<<grid_for(runs, 256), 256, 0, st>>>(pts_sorted.p, sc.starts.p, sc.counts.p, runs, inv_res, key_mode, table.p, mask);
     FLS_CUDA(cudaGetLastError());
     n_pts = n;
     n_vox = (size_t)runs;
@@ -143,4 +143,25 @@ int IvoxMap::append_and_build(const float4* d_new, size_t n_new, long long capac
     return FLS_OK;
 }
 
+}  // namespace fls
+
+namespace fls {
+namespace {
+__global__ void transform_f_kernel(const float4* __restrict__ in, size_t n, float r0, float r1, float r2, float r3, float r4, float r5, float r6,
+                                   float r7, float r8, float t0, float t1, float t2, float4* __restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = in[i];
+    out[i] = make_float4(xform_row_f(r0, r1, r2, t0, p.x, p.y, p.z), xform_row_f(r3, r4, r5, t1, p.x, p.y, p.z),
+                         xform_row_f(r6, r7, r8, t2, p.x, p.y, p.z), p.w);
+}
+}  // namespace
+
+void launch_transform_f(const float4* d_in, size_t n, const double* T, float4* d_out, cudaStream_t st) {
+    if (n == 0) return;
+    // T column-major: R(r,c) = T[c*4+r]
+    transform_f_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, n, (float)T[0], (float)T[4], (float)T[8], (float)T[1], (float)T[5],
+                                                                   (float)T[9], (float)T[2], (float)T[6], (float)T[10], (float)T[12],
+                                                                   (float)T[13], (float)T[14], d_out);
+}
 }  // namespace fls

@@ -4,20 +4,27 @@
 
 namespace fls {
 
-// scratch shared by the sort / run-length passes of every map build
+// scratch shared by the sort / run-length passes of every map build and of the voxel-grid filter
 struct BuildScratch {
     DevBuf<unsigned long long> keys, keys_sorted, uniq;
-    DevBuf<unsigned> idx, idx_sorted, counts, starts;
+    DevBuf<unsigned> idx, idx_sorted, counts, starts, k32a, k32b, uniq32;
     DevBuf<unsigned char> cub_tmp;
+    DevBuf<float> minmax;
     DevBuf<int> num_runs;
     int* h_num_runs = nullptr;  // pinned
     BuildScratch();
     ~BuildScratch();
 };
 
-// iVox map: voxel-contiguous float4 points + open-addressing table (see fls_ivox.cuh)
+// K7: VoxelGridCloud on the device.  d_out must hold n records; returns the output count.
+size_t voxel_grid_device(const float4* d_pts, size_t n, float leaf, float4* d_out, BuildScratch& sc, cudaStream_t st, int* launches);
+
+// Point grid: voxel-contiguous float4 points + open-addressing table of {key, start, count} (see fls_ivox.cuh).
+// key_mode 0: round(p/res)  — IVoxMap::Pos2Grid (iVox map of the LOAM plug-in)
+// key_mode 1: floor(p/res)  — uniform search grid under the bounded exact 1-NN of IcpOptimized / GetFitnessScore
 struct IvoxMap {
     float res = 0.5f, inv_res = 2.0f;
+    int key_mode = 0;
     size_t n_pts = 0, n_vox = 0;
     unsigned mask = 0;
     DevBuf<float4> pts_all;     // insertion order (kept so incremental adds can rebuild)
@@ -36,7 +43,62 @@ struct IvoxMap {
     size_t bytes() const { return pts_all.bytes() + pts_sorted.bytes() + table.bytes(); }
 };
 
-// repack caller records (stride 16 or >= 20 with intensity at byte 16) into packed float4 on the device
+// ---- NDT voxel map ------------------------------------------------------------------------------------------
+// Hot record read by the residual kernel: mean + symmetric information matrix (upper triangle), 80 bytes.
+struct __align__(16) NdtHot {
+    double mu[3];
+    double info[6];  // xx, xy, xz, yy, yz, zz
+    double pad;
+};
+// Cold per-voxel state used only by AddCloudToLocalMap / UpdateVoxel (incremental_ndt.h:130-179 upstream)
+struct NdtCold {
+    double sigma[9];
+    int num_points;   // VoxelData::num_points_
+    int carry_count;  // points buffered and not yet consumed by an estimate (<= min_points_in_voxel)
+    int estimated;
+    int pad;
+};
+// table slot: {packed key, voxel index, estimated flag}
+struct NdtView {
+    const HashSlot* __restrict__ tab;
+    const NdtHot* __restrict__ hot;
+    unsigned mask;
+    double inv_voxel;
+};
+
+struct NdtMap {
+    double voxel = 1.0, inv_voxel = 1.0;
+    int min_pts = 5, max_pts = 50;
+    long long capacity = 100000;
+    size_t n_vox = 0;
+    unsigned mask = 0;
+    size_t slots = 0;
+    DevBuf<HashSlot> table;
+    DevBuf<NdtHot> hot;
+    DevBuf<NdtCold> cold;
+    DevBuf<double> carry;  // [capacity][min_pts][3]
+    DevBuf<float4> filtered;
+    DevBuf<int> counter;  // device voxel counter
+    BuildScratch scratch;
+    int launches = 0;
+
+    void configure(double voxel_size, int min_points, int max_points, long long cap);
+    // VoxelGridCloud(cloud, leaf) then insert/update voxels; `first_scan` = flag_first_scan_ upstream
+    int add_cloud(const float4* d_cloud, size_t n, float leaf, bool first_scan, cudaStream_t st);
+    NdtView view() const {
+        NdtView v;
+        v.tab = table.p;
+        v.hot = hot.p;
+        v.mask = mask;
+        v.inv_voxel = inv_voxel;
+        return v;
+    }
+    size_t bytes() const { return table.bytes() + hot.bytes() + cold.bytes() + carry.bytes(); }
+};
+
+// repack caller records (stride >= 20, intensity at byte 16) into packed float4 on the device
 void launch_repack(const unsigned char* d_raw, size_t n, size_t stride, float4* d_out, cudaStream_t st);
+// TransformPointCloud(cloud, Mat4d) with R, t cast to float first (pointcloud_utility.h:141-158 upstream); T column-major
+void launch_transform_f(const float4* d_in, size_t n, const double* T_colmajor, float4* d_out, cudaStream_t st);
 
 }  // namespace fls
