@@ -88,6 +88,20 @@ def test_match_64line(scene64):
     assert dt < POS_TOL and dr < ROT_TOL, (dt, dr)
 
 
+def test_fitness_score_localization(scene16):
+    cfg = default_config(FLS_P2PLANE_IVOX)
+    g, o = _pair(cfg)
+    g.AddCloudToLocalMap([scene16["map"]])
+    o.add_cloud(scene16["map"])
+    from funny_lidar_slam_b200.registration import PointcloudCluster
+    Tg = scene16["guess"].copy()
+    g.Match(PointcloudCluster(planar_cloud=scene16["scan"]), Tg)
+    o.match(scene16["scan"], scene16["guess"])
+    for r in (1.0, 2.0):
+        fo, fg = o.fitness(r), g.GetFitnessScore(r)
+        assert abs(fg - fo) <= 1e-5 * max(1.0, abs(fo)), (r, fg, fo)
+
+
 def test_match_failure_paths(scene16):
     """empty scan / scan far from the map: Match returns false, T still written (loam_point_to_plane_ivox.h:198-203)."""
     cfg = default_config(FLS_P2PLANE_IVOX)
