@@ -71,16 +71,17 @@ def test_streaming_mapping_mode(world, traj):
     g.AddCloudToLocalMap([first_w])
     o.add_cloud(first_w)
     assert g.map_info().n_voxels == o.map_voxels
-    Tprev_g, Tprev_o = traj[0].copy(), traj[0].copy()
-    for k in range(1, 5):
+    Tg = traj[0].copy()
+    for k in range(1, 6):
         scan = synth.make_scan(world, traj[k], "vlp16", seed=40 + k)["points"]
-        Tg = Tprev_g.copy()
+        # stand-in for the IMU / constant-velocity prediction of FrontEnd::Run (frontend.cpp:191-205 upstream)
+        guess = synth.perturb_pose(traj[k], seed=400 + k, dpos=0.05, drot_deg=0.5)
+        Tg = guess.copy()
         ok_g = g.Match(_cluster(scan), Tg)
-        ok_o, To, st_o = o.match(scan, Tprev_o)
+        ok_o, To, st_o = o.match(scan, guess)
         assert ok_g == ok_o, k
         assert g.last_stats.iterations == st_o.iterations, k
         dt, dr = synth.pose_error(Tg, To)
         assert dt < POS_TOL and dr < ROT_TOL, (k, dt, dr)
         assert g.map_info().n_voxels == o.map_voxels, k
-        Tprev_g, Tprev_o = Tg, To
-    assert synth.pose_error(Tprev_g, traj[4])[0] < 0.15
+    assert synth.pose_error(Tg, traj[5])[0] < 0.05
