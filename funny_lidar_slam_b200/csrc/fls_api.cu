@@ -26,6 +26,10 @@ Handle::Handle(const fls_config& c) : cfg(c) {
     fit_out.reserve(2);
     ivox.set_resolution(cfg.ivox_resolution);
     ivox.key_mode = 0;
+    {
+        static const int counts[4] = {1, 7, 19, 27};
+        ivox.n_stencil = counts[cfg.ivox_nearby];
+    }
     ndt.configure(cfg.ndt_voxel_size, cfg.ndt_min_points_in_voxel, cfg.ndt_max_points_in_voxel, cfg.ndt_capacity);
     // search grid of the bounded exact 1-NN: cell >= sqrt(max_correspond_distance)  [quirk 4]
     icp_grid.key_mode = 1;
@@ -79,6 +83,9 @@ IvoxView Handle::grid_view(const IvoxMap& g) const {
     v.max_range2 = cfg.ivox_max_range * cfg.ivox_max_range;
     static const int counts[4] = {1, 7, 19, 27};
     v.n_stencil = counts[cfg.ivox_nearby];
+    v.lists = g.lists.p;
+    v.ctab = g.ctab.p;
+    v.cmask = g.cmask;
     return v;
 }
 IvoxView Handle::ivox_view() const { return grid_view(ivox); }
@@ -87,6 +94,7 @@ void Handle::begin_call() {
     FLS_CUDA(cudaSetDevice(cfg.device));
     launches = 0;
     h2d_bytes = d2h_bytes = 0;
+    fused_loop = false;
     FLS_CUDA(cudaEventRecord(ev0, stream));
 }
 
@@ -145,16 +153,20 @@ int Handle::add_cloud_ivox(const void* pts, size_t n, size_t stride) {
 int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st) {
     if (ivox.n_pts == 0) return FLS_ERR_NO_MAP;
     const int ni = (int)n;
-    const int grid = p2plane_grid(ni);
+    const int grid = p2plane_grid(ni, cfg.device);
     rec0.reserve(n);
     rec1.reserve(n);
     flags.reserve(n);
-    partials.reserve((size_t)(grid > 0 ? grid : 1) * kAccStride);
+    src_f.reserve(n);
+    partials.reserve((size_t)grid * kAccStride);
     if (n) FLS_CUDA(cudaMemsetAsync(flags.p, 0, n, stream));
     launch_gn_init(state.p, T, stream);
     launches++;
-    P2PlaneArgs a;
-    a.src = d_src;
+    // Morton-order the queries by the voxel they fall into at the initial pose (locality only: the sums are order-free
+    // up to fp64 rounding, and the persistent per-point records live in the same order for the whole Match)
+    sort_queries(d_src, ni, state.p, ivox.inv_res, src_f.p, scratch, stream, &launches);
+    P2PlaneLoopArgs a;
+    a.src = src_f.p;
     a.n = ni;
     a.map = ivox_view();
     a.plane_thres = cfg.point_to_planar_thres;
@@ -163,12 +175,24 @@ int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* co
     a.rec1 = rec1.p;
     a.flags = flags.p;
     a.partials = partials.p;
-    // roofline accounting: 16 B source point + n_stencil x 16 B slot probes + 32 B persistent
-    // record per point-iteration, 16 B per map record resident in the hit voxels.
+    a.gp.method = FLS_P2PLANE_IVOX;
+    a.gp.max_iterations = cfg.max_iterations;
+    a.gp.min_effective = 50;
+    a.gp.n_blocks = grid;
+    a.gp.rot_thres = cfg.rotation_converge_thres;
+    a.gp.pos_thres = cfg.position_converge_thres;
+    a.log = log.p;
+    a.log_cap = log_cap;
+    // roofline accounting (SURVEY.md §8d, K1 — the REFERENCE algorithm's traffic): 16 B source point + n_stencil x 16 B
+    // slot probes + 32 B persistent record per point-iteration, 16 B per map record resident in the stencil voxels.
     per_point_iter_bytes = 16 + 16LL * a.map.n_stencil + 32;
     per_cand_bytes = 16;
     per_hit_bytes = 0;
-    gn_loop(*this, FLS_P2PLANE_IVOX, grid, 50, [&] { launch_p2plane_iter(a, stream); });
+    if (profile) FLS_CUDA(cudaEventRecord(prof_ev[0], stream));
+    launch_p2plane_loop(a, grid, stream);
+    if (profile) FLS_CUDA(cudaEventRecord(prof_ev[1], stream));
+    launches++;
+    fused_loop = true;
     last_src = d_src;
     last_src_n = n;
     return finish_match(T, converged, st, (long long)n);
@@ -382,13 +406,14 @@ int Handle::finish_match(double* T, int* converged, fls_match_stats* st, long lo
         st->sum_residual = s.sum_res;
         if (profile) {
             float tot = 0.f;
-            for (int it = 0; it < s.iter && 2 * it + 1 < (int)prof_ev.size(); ++it) {
+            const int n_timed = fused_loop ? 1 : s.iter;  // fused: one launch runs every iteration
+            for (int it = 0; it < n_timed && 2 * it + 1 < (int)prof_ev.size(); ++it) {
                 float ms = 0.f;
                 FLS_CUDA(cudaEventElapsedTime(&ms, prof_ev[2 * it], prof_ev[2 * it + 1]));
                 tot += ms;
             }
             st->kernel_ms = tot;
-            st->kernel_launches = s.iter;
+            st->kernel_launches = n_timed;
             st->algo_bytes = (long long)s.iter * n_source * per_point_iter_bytes + (long long)(s.cand_total + 0.5) * per_cand_bytes +
                              (long long)(s.hits_total + 0.5) * per_hit_bytes;
         }

@@ -1,12 +1,20 @@
-// fls_gn.cuh — Gauss-Newton plumbing shared by the three residual kernels: the per-block reduction of the
-// 29 accumulators and the launch interface of the device-side solve / pose update (K6).
+// fls_gn.cuh — Gauss-Newton plumbing shared by the residual kernels: the per-block reduction of the
+// accumulators and the device-side solve / pose update / stop rule (K6).
+//
+// Conventions per plug-in (all line numbers upstream):
+//   LOAM p2plane : dx=[dθ,dt], R <- Exp(dθ)·R, full-pivot solve, stop on thresholds OR |Δ‖dx‖|<1e-4,
+//                  fail when n_valid < 50                      (loam_point_to_plane_ivox.h:167-203)
+//   NDT          : dx=[dθ,dt], R <- R·Exp(dθ), H^-1·err, stop on thresholds, result forced true,
+//                  early-out false when effective < min        (incremental_ndt.h:306-325)
+//   ICP          : dx=[dt,dθ], R <- R·Exp(dθ), det==0 -> skip, converged only if thresholds met
+//                                                              (icp_optimized.h:129-149)
 #pragma once
 #include "fls_common.cuh"
 
 namespace fls {
 
 struct GnParams {
-    int method;  // fls_method: selects dx layout, update side, solver, stop rule (SURVEY.md §8a convention table)
+    int method;  // fls_method: selects dx layout, update side, solver, stop rule
     int max_iterations;
     int min_effective;  // NDT: min_effective_pts; LOAM: 50 valid planar points
     int n_blocks;       // rows of the partial-sum matrix produced by the residual kernel
@@ -38,6 +46,84 @@ __device__ __forceinline__ void block_reduce_store(double (&acc)[kNumAcc], doubl
         for (int w = 0; w < W; ++w) v += s_red[w][threadIdx.x];
         partial_row[threadIdx.x] = v;
     }
+}
+
+// One Gauss-Newton step from the reduced totals `tot[kNumAcc]`: fills H/g, solves, updates the pose in `s`,
+// applies the plug-in's stop rule.  Executed by a single thread.
+__device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p, fls_iter_log* log, int log_cap) {
+    double H[36], g[6], dx[6] = {0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < 6; ++r)
+        for (int c = r; c < 6; ++c) H[r * 6 + c] = H[c * 6 + r] = tot[tri6(r, c)];
+    for (int a = 0; a < 6; ++a) g[a] = tot[21 + a];
+    const long long n_valid = (long long)(tot[kAccValid] + 0.5);
+    const double sum_res = tot[kAccRes];
+    for (int i = 0; i < 36; ++i) s->H[i] = H[i];
+    for (int i = 0; i < 6; ++i) s->g[i] = g[i];
+    s->n_valid = n_valid;
+    s->sum_res = sum_res;
+    s->cand_total += tot[kAccCand];
+    s->hits_total += tot[kAccHits];
+    const int it = s->iter;
+    s->iter = it + 1;
+    for (int i = 0; i < 9; ++i) s->Rprev[i] = s->R[i];
+    for (int i = 0; i < 3; ++i) s->tprev[i] = s->t[i];
+
+    bool stop = false;
+    if (p.method == FLS_NDT && n_valid < (long long)p.min_effective) {
+        s->failed = 1;  // incremental_ndt.h:306-309 — T = pose, return false
+        s->converged = 0;
+        stop = true;
+    } else {
+        double Rd[9], Rn[9];
+        if (p.method == FLS_ICP_P2P) {
+            const double det = solve6_lu(H, g, dx);
+            if (det == 0.0) {
+                for (int i = 0; i < 6; ++i) dx[i] = 0;  // icp_optimized.h:129-131 `continue`
+            } else {
+                for (int a = 0; a < 3; ++a) s->t[a] += dx[a];
+                so3_exp(dx + 3, Rd);
+                mat3_mul(s->R, Rd, Rn);
+                for (int i = 0; i < 9; ++i) s->R[i] = Rn[i];
+                if (norm3(dx + 3) < p.rot_thres && norm3(dx) < p.pos_thres) {
+                    s->converged = 1;
+                    stop = true;
+                }
+            }
+        } else if (p.method == FLS_NDT) {
+            solve6_lu(H, g, dx);
+            so3_exp(dx, Rd);
+            mat3_mul(s->R, Rd, Rn);
+            for (int i = 0; i < 9; ++i) s->R[i] = Rn[i];
+            for (int a = 0; a < 3; ++a) s->t[a] += dx[3 + a];
+            if (norm3(dx) < p.rot_thres && norm3(dx + 3) < p.pos_thres) stop = true;
+            s->converged = 1;  // forced true after the loop (incremental_ndt.h:325)
+        } else {
+            solve6_fullpiv(H, g, dx);
+            so3_exp(dx, Rd);
+            mat3_mul(Rd, s->R, Rn);
+            for (int i = 0; i < 9; ++i) s->R[i] = Rn[i];
+            for (int a = 0; a < 3; ++a) s->t[a] += dx[3 + a];
+            const double rn = norm3(dx), pn = norm3(dx + 3);
+            const double drot = fabs(rn - s->last_rot), dpos = fabs(pn - s->last_pos);
+            s->last_rot = rn;
+            s->last_pos = pn;
+            if ((rn < p.rot_thres && pn < p.pos_thres) || (drot < 1.0e-4 && dpos < 1.0e-4)) stop = true;
+            s->converged = (n_valid >= (long long)p.min_effective) ? 1 : 0;  // :201-203
+        }
+        for (int i = 0; i < 6; ++i) s->dx[i] = dx[i];
+        if (it + 1 >= p.max_iterations) stop = true;
+    }
+    if (log && it < log_cap) {
+        fls_iter_log& L = log[it];
+        for (int i = 0; i < 36; ++i) L.H[i] = H[i];
+        for (int i = 0; i < 6; ++i) {
+            L.g[i] = g[i];
+            L.dx[i] = dx[i];
+        }
+        L.sum_residual = sum_res;
+        L.n_valid = n_valid;
+    }
+    if (stop) s->done = 1;
 }
 #endif
 

@@ -37,6 +37,7 @@ struct Handle {
     double T_final[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     std::vector<cudaEvent_t> prof_ev;  // FLS_FLAG_PROFILE: 2 events per iteration around the residual kernel
     bool profile = false;
+    bool fused_loop = false;  // the last Match ran its whole GN loop in one launch
     long long per_point_iter_bytes = 0;  // fixed part of the algorithmic bytes per point-iteration (set by match_*)
     long long per_cand_bytes = 0;        // bytes per scanned map record
     long long per_hit_bytes = 0;         // bytes per table probe that hit (NDT voxel record)

@@ -1,6 +1,7 @@
 // fls_kernels.h — launch interfaces of the residual kernels (K1 p2plane/iVox, K2 NDT, K3 ICP) and GetFitnessScore.
 #pragma once
 #include "fls_common.cuh"
+#include "fls_gn.cuh"
 #include "fls_ivox.cuh"
 #include "fls_maps.h"
 
@@ -10,8 +11,9 @@ static constexpr int kP2PlaneBlock = 128;
 static constexpr int kNdtBlock = 128;
 static constexpr int kIcpBlock = 128;
 
-struct P2PlaneArgs {
-    const float4* __restrict__ src;  // body-frame scan, packed float4
+// whole-loop arguments of the persistent LoamPointToPlaneIVOX kernel (K1 + fused K6)
+struct P2PlaneLoopArgs {
+    const float4* __restrict__ src;  // body-frame scan in Morton order of the query voxel, packed float4
     int n;
     IvoxView map;
     double plane_thres;
@@ -20,9 +22,14 @@ struct P2PlaneArgs {
     float4* __restrict__ rec1;  //                              J4, J5, |d|, 1
     unsigned char* __restrict__ flags;
     double* __restrict__ partials;  // [grid][kAccStride]
+    GnParams gp;
+    fls_iter_log* log;
+    int log_cap;
 };
-int p2plane_grid(int n);
-void launch_p2plane_iter(const P2PlaneArgs& a, cudaStream_t st);
+int p2plane_grid(int n, int device);
+void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st);
+void sort_queries(const float4* d_src, int n, const GnState* d_state, float inv_res, float4* d_sorted, BuildScratch& sc, cudaStream_t st,
+                  int* launches);
 void launch_ivox_knn_test(const IvoxView& map, const float4* d_q, int n, float4* d_out, int* d_found, cudaStream_t st);
 
 struct NdtArgs {

@@ -22,14 +22,28 @@ size_t voxel_grid_device(const float4* d_pts, size_t n, float leaf, float4* d_ou
 // Point grid: voxel-contiguous float4 points + open-addressing table of {key, start, count} (see fls_ivox.cuh).
 // key_mode 0: round(p/res)  — IVoxMap::Pos2Grid (iVox map of the LOAM plug-in)
 // key_mode 1: floor(p/res)  — uniform search grid under the bounded exact 1-NN of IcpOptimized / GetFitnessScore
+//
+// With n_stencil > 0 the build also materialises, for every "centre" voxel (occupied, or within the stencil of an
+// occupied voxel), the concatenation of the points of its stencil voxels in the reference's visit order — the exact
+// candidate sequence IVoxMap::GetClosestPoint walks — as one contiguous float4 run, plus a second table
+// {centre key -> run start, run length}.  A k-NN query is then ONE table probe and ONE streaming scan
+// (HBM is spent to buy bandwidth-friendly access: ~n_stencil x the point array).
 struct IvoxMap {
     float res = 0.5f, inv_res = 2.0f;
     int key_mode = 0;
+    int n_stencil = 0;  // 0: no stencil lists (ICP / fitness grids)
     size_t n_pts = 0, n_vox = 0;
     unsigned mask = 0;
     DevBuf<float4> pts_all;     // insertion order (kept so incremental adds can rebuild)
     DevBuf<float4> pts_sorted;  // voxel-contiguous, Morton order
-    DevBuf<HashSlot> table;
+    DevBuf<HashSlot> table;     // occupied voxels
+    // stencil lists
+    size_t n_centers = 0, n_list = 0;
+    unsigned cmask = 0;
+    DevBuf<float4> lists;
+    DevBuf<HashSlot> ctab;
+    DevBuf<unsigned long long> ckeys, ckeys_sorted, cuniq;
+    DevBuf<unsigned> ccount, cstart;
     BuildScratch scratch;
     int launches = 0;
 
@@ -37,10 +51,11 @@ struct IvoxMap {
         res = r;
         inv_res = 1.0f / r;
     }
-    void clear() { n_pts = n_vox = 0; }
+    void clear() { n_pts = n_vox = n_centers = n_list = 0; }
     // append n points that are already on the device (packed float4) and rebuild; returns fls_status
     int append_and_build(const float4* d_new, size_t n_new, long long capacity, cudaStream_t st);
-    size_t bytes() const { return pts_all.bytes() + pts_sorted.bytes() + table.bytes(); }
+    int build_stencil_lists(cudaStream_t st);
+    size_t bytes() const { return pts_all.bytes() + pts_sorted.bytes() + table.bytes() + lists.bytes() + ctab.bytes(); }
 };
 
 // ---- NDT voxel map ------------------------------------------------------------------------------------------
