@@ -2,7 +2,9 @@
 // each plug-in's Match / AddCloudToLocalMap / GetFitnessScore.  The Gauss-Newton loop itself runs on the
 // device (residual kernel + gn_solve kernel per iteration, convergence decided on the device); the host
 // enqueues the iteration cap and reads the ~1 KB state block back once.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -158,7 +160,11 @@ int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* co
     rec1.reserve(n);
     flags.reserve(n);
     src_f.reserve(n);
-    partials.reserve((size_t)grid * kAccStride);
+    partials.reserve(p2plane_partials_len(ni));
+    // {next chunk, CTAs arrived} per iteration, the release flag, one self-resetting counter per chunk group
+    const size_t n_sync = 2 * (size_t)cfg.max_iterations + 1 + (size_t)p2plane_groups(ni) + 1;
+    sync_buf.reserve(n_sync);
+    FLS_CUDA(cudaMemsetAsync(sync_buf.p, 0, n_sync * sizeof(int), stream));
     if (n) FLS_CUDA(cudaMemsetAsync(flags.p, 0, n, stream));
     launch_gn_init(state.p, T, stream);
     launches++;
@@ -175,6 +181,15 @@ int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* co
     a.rec1 = rec1.p;
     a.flags = flags.p;
     a.partials = partials.p;
+    a.sync = sync_buf.p;
+    a.sync_flag = sync_buf.p + 2 * (size_t)cfg.max_iterations;
+    a.dbg_cta = nullptr;
+    if (std::getenv("FLS_DEBUG_TIMING")) {
+        dbg_cta.reserve((size_t)grid * 4 * 5);
+        FLS_CUDA(cudaMemsetAsync(dbg_cta.p, 0, (size_t)grid * 4 * 5 * sizeof(unsigned long long), stream));
+        a.dbg_cta = dbg_cta.p;
+        dbg_grid = grid;
+    }
     a.gp.method = FLS_P2PLANE_IVOX;
     a.gp.max_iterations = cfg.max_iterations;
     a.gp.min_effective = 50;
@@ -389,6 +404,47 @@ int Handle::finish_match(double* T, int* converged, fls_match_stats* st, long lo
     }
     end_call(st);
     const GnState& s = *h_state;
+    if (fused_loop && std::getenv("FLS_DEBUG_TIMING") && dbg_grid > 0 && s.iter > 1) {
+        std::vector<unsigned long long> h((size_t)dbg_grid * 4 * 5);
+        cudaMemcpy(h.data(), dbg_cta.p, h.size() * 8, cudaMemcpyDeviceToHost);
+        {
+            const int nw = dbg_grid * 4;
+            std::vector<int> order(nw);
+            for (int i = 0; i < nw; ++i) order[i] = i;
+            const unsigned long long* w = h.data() + (size_t)dbg_grid * 4;
+            std::sort(order.begin(), order.end(), [&](int x, int y) { return w[x * 4] < w[y * 4]; });
+            for (double q : {0.0, 0.25, 0.5, 0.75, 0.9, 0.99, 1.0}) {
+                const int k = order[(size_t)(q * (nw - 1))];
+                std::fprintf(stderr, "[fls timing] warp pct %.2f: point phase %llu cyc (knn %llu) | max list %llu, mean list %.1f\n", q, w[k * 4],
+                             w[k * 4 + 1], w[k * 4 + 2], w[k * 4 + 3] / 32.0);
+            }
+        }
+        const unsigned long long t0 = s.dbg[1][0];
+        std::vector<double> st, w0, wl, ar;
+        for (int b = 0; b < dbg_grid; ++b) {
+            st.push_back((double)(long long)(h[b * 4 + 0] - t0) * 1e-3);
+            w0.push_back((double)(long long)(h[b * 4 + 1] - t0) * 1e-3);
+            wl.push_back((double)(long long)(h[b * 4 + 2] - t0) * 1e-3);
+            ar.push_back((double)(long long)(h[b * 4 + 3] - t0) * 1e-3);
+        }
+        auto pct = [](std::vector<double> v, double q) {
+            std::sort(v.begin(), v.end());
+            return v[(size_t)(q * (v.size() - 1))];
+        };
+        std::fprintf(stderr, "[fls timing] it1 per-CTA (us from it start): start p0/50/100 %.1f %.1f %.1f | warp0 done %.1f %.1f %.1f | warpL done %.1f %.1f %.1f | cta done %.1f %.1f %.1f\n",
+                     pct(st, 0), pct(st, .5), pct(st, 1), pct(w0, 0), pct(w0, .5), pct(w0, 1), pct(wl, 0), pct(wl, .5), pct(wl, 1), pct(ar, 0),
+                     pct(ar, .5), pct(ar, 1));
+    }
+    if (fused_loop && std::getenv("FLS_DEBUG_TIMING")) {
+        std::fprintf(stderr, "[fls timing] iters %d  candidates/pt-iter %.1f  qr-fallback points/iter %.0f of %lld\n", s.iter,
+                     s.cand_total / (double)(n_source * (s.iter > 0 ? s.iter : 1)), s.hits_total / (double)(s.iter > 0 ? s.iter : 1), n_source);
+        for (int it = 0; it < s.iter && it < 16; ++it) {
+            const unsigned long long* d = s.dbg[it];
+            std::fprintf(stderr, "[fls timing] it %d: work %.1f us | reduce %.1f us | solve %.1f us | to next start %.1f us\n", it,
+                         (d[1] - d[0]) * 1e-3, (d[2] - d[1]) * 1e-3, (d[3] - d[2]) * 1e-3,
+                         (it + 1 < s.iter && it + 1 < 16) ? (s.dbg[it + 1][0] - d[3]) * 1e-3 : 0.0);
+        }
+    }
     for (int r = 0; r < 3; ++r) {
         for (int c = 0; c < 3; ++c) T[c * 4 + r] = s.R[r * 3 + c];
         T[12 + r] = s.t[r];
@@ -720,9 +776,16 @@ int fls_voxel_grid(int device, const void* pts, size_t n, size_t stride, float l
 int fls_extract_features(const fls_feature_cfg* cfg, const float* depth, const int32_t* col, size_t n, const int32_t* row_start,
                          const int32_t* row_end, int32_t n_rows, int32_t* corner_idx, size_t* n_corner, int32_t* planar_idx, size_t* n_planar,
                          fls_match_stats* stats) {
-    (void)cfg; (void)depth; (void)col; (void)n; (void)row_start; (void)row_end; (void)n_rows; (void)corner_idx; (void)n_corner; (void)planar_idx;
-    (void)n_planar; (void)stats;
-    return FLS_ERR_UNSUPPORTED;
+    if (!cfg || !depth || !col || !row_start || !row_end || !corner_idx || !n_corner || !planar_idx || !n_planar || n_rows < 0)
+        return FLS_ERR_INVALID_ARG;
+    // the reference CHECK_NE()s both thresholds against FloatNaN (feature_extractor.cpp:19-20)
+    if (!(cfg->corner_threshold < 3.0e38f) || !(cfg->planar_threshold < 3.0e38f)) return FLS_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return FLS_ERR_NO_DEVICE;
+    FLS_TRY
+    return fls::extract_features_device(cfg->device, depth, col, n, row_start, row_end, n_rows, cfg->corner_threshold, cfg->planar_threshold,
+                                        corner_idx, n_corner, planar_idx, n_planar, stats);
+    FLS_CATCH
 }
 
 }  // extern "C"

@@ -157,6 +157,9 @@ struct GnState {
     int converged;  // value Match returns
     int failed;     // early-out (NDT effective_num < min)
     int pad[2];
+    // device-side phase timestamps (globaltimer ns) of the fused LOAM loop, first 16 iterations:
+    // [it][0] iteration start, [1] last CTA arrived, [2] partials reduced, [3] solved + released
+    unsigned long long dbg[16][4];
 };
 
 // upper-triangular index of a symmetric 6x6 (row <= col)
@@ -246,6 +249,74 @@ __host__ __device__ inline void solve6_fullpiv(const double* H, const double* g,
     }
     for (int i = 0; i < 6; ++i) x[i] = 0;
     for (int i = 0; i < rank; ++i) x[cperm[i]] = y[i];
+}
+
+// Fast path for the well-conditioned symmetric positive-definite case (H = sum J^T J): fully unrolled LDL^T with the
+// 21 upper-triangular entries in registers.  Returns false — caller falls back to the pivoting solver that mirrors the
+// reference's rank handling — when a pivot is not safely positive (min pivot <= 1e-8 * max pivot).
+// Also returns the determinant (product of pivots) for IcpOptimized's `det == 0` test.
+__host__ __device__ inline bool solve6_spd(const double* H, const double* g, double* x, double* det_out) {
+    double a00 = H[0], a01 = H[1], a02 = H[2], a03 = H[3], a04 = H[4], a05 = H[5];
+    double a11 = H[7], a12 = H[8], a13 = H[9], a14 = H[10], a15 = H[11];
+    double a22 = H[14], a23 = H[15], a24 = H[16], a25 = H[17];
+    double a33 = H[21], a34 = H[22], a35 = H[23];
+    double a44 = H[28], a45 = H[29];
+    double a55 = H[35];
+    double b0 = g[0], b1 = g[1], b2 = g[2], b3 = g[3], b4 = g[4], b5 = g[5];
+    double dmax = fmax(fmax(fmax(a00, a11), fmax(a22, a33)), fmax(a44, a55));
+    if (!(dmax > 0.0)) return false;
+    const double tiny = 1e-8 * dmax;
+    // elimination of column 0
+    if (!(a00 > tiny)) return false;
+    double inv = 1.0 / a00;
+    double l1 = a01 * inv, l2 = a02 * inv, l3 = a03 * inv, l4 = a04 * inv, l5 = a05 * inv;
+    a11 -= l1 * a01; a12 -= l1 * a02; a13 -= l1 * a03; a14 -= l1 * a04; a15 -= l1 * a05;
+    a22 -= l2 * a02; a23 -= l2 * a03; a24 -= l2 * a04; a25 -= l2 * a05;
+    a33 -= l3 * a03; a34 -= l3 * a04; a35 -= l3 * a05;
+    a44 -= l4 * a04; a45 -= l4 * a05;
+    a55 -= l5 * a05;
+    b1 -= l1 * b0; b2 -= l2 * b0; b3 -= l3 * b0; b4 -= l4 * b0; b5 -= l5 * b0;
+    // column 1
+    if (!(a11 > tiny)) return false;
+    inv = 1.0 / a11;
+    l2 = a12 * inv; l3 = a13 * inv; l4 = a14 * inv; l5 = a15 * inv;
+    a22 -= l2 * a12; a23 -= l2 * a13; a24 -= l2 * a14; a25 -= l2 * a15;
+    a33 -= l3 * a13; a34 -= l3 * a14; a35 -= l3 * a15;
+    a44 -= l4 * a14; a45 -= l4 * a15;
+    a55 -= l5 * a15;
+    b2 -= l2 * b1; b3 -= l3 * b1; b4 -= l4 * b1; b5 -= l5 * b1;
+    // column 2
+    if (!(a22 > tiny)) return false;
+    inv = 1.0 / a22;
+    l3 = a23 * inv; l4 = a24 * inv; l5 = a25 * inv;
+    a33 -= l3 * a23; a34 -= l3 * a24; a35 -= l3 * a25;
+    a44 -= l4 * a24; a45 -= l4 * a25;
+    a55 -= l5 * a25;
+    b3 -= l3 * b2; b4 -= l4 * b2; b5 -= l5 * b2;
+    // column 3
+    if (!(a33 > tiny)) return false;
+    inv = 1.0 / a33;
+    l4 = a34 * inv; l5 = a35 * inv;
+    a44 -= l4 * a34; a45 -= l4 * a35;
+    a55 -= l5 * a35;
+    b4 -= l4 * b3; b5 -= l5 * b3;
+    // column 4
+    if (!(a44 > tiny)) return false;
+    inv = 1.0 / a44;
+    l5 = a45 * inv;
+    a55 -= l5 * a45;
+    b5 -= l5 * b4;
+    if (!(a55 > tiny)) return false;
+    // back substitution on the upper-triangular factor
+    const double x5 = b5 / a55;
+    const double x4 = (b4 - a45 * x5) / a44;
+    const double x3 = (b3 - a34 * x4 - a35 * x5) / a33;
+    const double x2 = (b2 - a23 * x3 - a24 * x4 - a25 * x5) / a22;
+    const double x1 = (b1 - a12 * x2 - a13 * x3 - a14 * x4 - a15 * x5) / a11;
+    const double x0 = (b0 - a01 * x1 - a02 * x2 - a03 * x3 - a04 * x4 - a05 * x5) / a00;
+    x[0] = x0; x[1] = x1; x[2] = x2; x[3] = x3; x[4] = x4; x[5] = x5;
+    if (det_out) *det_out = a00 * a11 * a22 * a33 * a44 * a55;
+    return true;
 }
 
 // 6x6 partial-pivot LU solve; returns det (0 => x untouched).  Stands for `H.inverse() * b` and

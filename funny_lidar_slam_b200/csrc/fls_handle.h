@@ -29,6 +29,9 @@ struct Handle {
     DevBuf<float4> rec0, rec1;  // persistent per-point {J, |d|} records (LOAM plug-ins)
     DevBuf<unsigned char> flags;
     DevBuf<double> partials;
+    DevBuf<int> sync_buf;  // work / arrive counters + release flag of the persistent LOAM kernel
+    DevBuf<unsigned long long> dbg_cta;  // FLS_DEBUG_TIMING only
+    int dbg_grid = 0;
     DevBuf<GnState> state;
     GnState* h_state = nullptr;  // pinned
     DevBuf<fls_iter_log> log;

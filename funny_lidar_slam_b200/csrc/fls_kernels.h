@@ -21,12 +21,18 @@ struct P2PlaneLoopArgs {
     float4* __restrict__ rec0;  // persistent per-point record: J0..J3
     float4* __restrict__ rec1;  //                              J4, J5, |d|, 1
     unsigned char* __restrict__ flags;
-    double* __restrict__ partials;  // [grid][kAccStride]
+    double* __restrict__ partials;  // [chunks][kAccStride] — one row per 128-point chunk
+    int* sync;       // [2*max_iterations]: per iteration {next chunk to hand out, CTAs arrived}; zeroed per Match
+    int* sync_flag;  // iterations completed (release flag of the hand-over)
+    unsigned long long* dbg_cta;  // optional [grid][4] per-CTA timestamps of iteration 1 (FLS_DEBUG_TIMING), may be null
     GnParams gp;
     fls_iter_log* log;
     int log_cap;
 };
 int p2plane_grid(int n, int device);
+int p2plane_chunks(int n);            // warp-sized (32-point) work chunks
+int p2plane_groups(int n);            // groups of 32 chunks
+size_t p2plane_partials_len(int n);   // doubles in the partial-sum buffer (chunk rows + group rows)
 void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st);
 void sort_queries(const float4* d_src, int n, const GnState* d_state, float inv_res, float4* d_sorted, BuildScratch& sc, cudaStream_t st,
                   int* launches);

@@ -111,6 +111,11 @@ struct NdtMap {
     size_t bytes() const { return table.bytes() + hot.bytes() + cold.bytes() + carry.bytes(); }
 };
 
+// K4: LOAM feature extraction on the projector's arrays (host in / host out); see fls_features.cu
+int extract_features_device(int device, const float* depth, const int* col, size_t n, const int* row_start, const int* row_end, int n_rows,
+                            float corner_thr, float planar_thr, int* corner_idx, size_t* n_corner, int* planar_idx, size_t* n_planar,
+                            fls_match_stats* stats);
+
 // repack caller records (stride >= 20, intensity at byte 16) into packed float4 on the device
 void launch_repack(const unsigned char* d_raw, size_t n, size_t stride, float4* d_out, cudaStream_t st);
 // TransformPointCloud(cloud, Mat4d) with R, t cast to float first (pointcloud_utility.h:141-158 upstream); T column-major

@@ -1,18 +1,25 @@
-// fls_p2plane.cu — K1 (+ fused K6): the whole LoamPointToPlaneIVOX Gauss-Newton loop as ONE persistent
-// cooperative kernel.
+// fls_p2plane.cu — K1 (+ fused K6): the whole LoamPointToPlaneIVOX Gauss-Newton loop as ONE persistent kernel.
 //
 // Per source point and iteration it fuses what LoamPointToPlaneIVOX::PlanerMatch / ::SumCoefficient do
 // (include/registration/loam_point_to_plane_ivox.h:256-340 upstream): transform with the current pose, bounded
 // 5-NN in the iVox map, least-squares plane through the 5 neighbours (column-pivoted Householder QR, fp64),
-// validity / near-point gates, J (6) and |d|, and the 21+6+2 Gauss-Newton sums; then, after a grid-wide barrier,
-// block 0 reduces the per-block partials in a fixed order, solves the 6x6 system, updates the pose and applies the
-// stop rule (:167-203), and a second barrier releases the next iteration.  No host round trip inside a Match.
+// validity / near-point gates, J (6) and |d|, and the 21+6+2 Gauss-Newton sums; the CTA that finishes an iteration
+// last reduces the partial sums in a fixed order, solves the 6x6 system, updates the pose and applies the stop
+// rule (:167-203), then releases the other CTAs into the next iteration.  No host round trip inside a Match.
 //
 // B200 mapping
-//   * grid = #SMs x resident CTAs (cooperative launch), grid-stride over points: no tail wave, no relaunch gaps;
+//   * grid = #SMs x resident CTAs, launched cooperatively only to guarantee co-residency; the scheduling unit is the
+//     WARP: each warp pulls 32-point chunks from an atomic counter (dense regions cost more than sparse ones) and
+//     there is no block-wide barrier inside the work loop;
+//   * every chunk writes its own row of 31 partial sums; the warp that completes a group of 32 chunks folds the group
+//     into one row, and the last CTA folds the ~100 group rows — all in fixed order, so the result does not depend
+//     on which warp processed which chunk (bitwise reproducible) and the serial tail is ~1 us;
+//   * iteration hand-over: arrive counter + release flag (one wait per iteration) instead of grid-wide barriers; the
+//     6x6 solve is a register-resident LDL^T (pivoting fallback for rank-deficient systems);
 //   * queries are processed in Morton order of their voxel (sorted once per Match), so the lanes of a warp share
 //     centre voxels: the table probe and the candidate stream are the same addresses -> L1 broadcast, no divergence;
-//   * k-NN = 1 probe of the centre table + a streaming scan of that centre's contiguous stencil list (fls_ivox.cuh);
+//   * k-NN = 1 probe of the centre table + a streaming scan of that centre's contiguous stencil list (fls_ivox.cuh),
+//     top-5 kept by a branch-free compare-exchange chain (half of all candidates enter the top-5 at list lengths ~25);
 //   * the 29 sums are accumulated warp-transposed: each lane stages {J, |d|, flags} in shared memory and lane k then
 //     owns sum k (32 FMAs on broadcast LDS) — one register pair of accumulator state instead of 62, no shuffles;
 //   * state that survives across iterations [quirk 1, SURVEY.md §7]: upstream resets the valid flags once per Match
@@ -26,41 +33,114 @@
 #include "fls_ivox.cuh"
 #include "fls_kernels.h"
 
-namespace cg = cooperative_groups;
-
 namespace fls {
 namespace {
 
-// Householder step on column K (rows K..4) of the 5x3 system, applied to the trailing columns and the rhs.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ---- branch-free top-5 ---------------------------------------------------------------------------------------------
+struct Top5 {
+    float d0, d1, d2, d3, d4;
+    unsigned j0, j1, j2, j3, j4;
+    __device__ __forceinline__ void init() {
+        d0 = d1 = d2 = d3 = d4 = INFINITY;
+        j0 = j1 = j2 = j3 = j4 = 0xffffffffu;
+    }
+#define FLS_CE(da, ja, db, jb)               \
+    {                                        \
+        const bool c_ = (db) < (da);         \
+        const float td_ = (da);              \
+        const unsigned tj_ = (ja);           \
+        (da) = c_ ? (db) : (da);             \
+        (ja) = c_ ? (jb) : (ja);             \
+        (db) = c_ ? td_ : (db);              \
+        (jb) = c_ ? tj_ : (jb);              \
+    }
+    // ascending (d, visit order): strict '<' everywhere, so a later candidate never passes an equal earlier one
+    __device__ __forceinline__ void push(float d, unsigned j) {
+        const bool c = d < d4;
+        d4 = c ? d : d4;
+        j4 = c ? j : j4;
+        FLS_CE(d3, j3, d4, j4)
+        FLS_CE(d2, j2, d3, j3)
+        FLS_CE(d1, j1, d2, j2)
+        FLS_CE(d0, j0, d1, j1)
+    }
+#undef FLS_CE
+};
+
+// IVoxMap::GetClosestPoint through the stencil lists: one probe of the centre table, then a streaming scan of the
+// contiguous candidate run (already in the reference's visit order).  Indices refer to `lists`.
+__device__ __forceinline__ void knn5_stream(const IvoxView& m, float qx, float qy, float qz, Top5& nn, unsigned& n_cand) {
+    nn.init();
+    n_cand = 0;
+    const unsigned long long key = pack_key(ivox_coord(qx, m.inv_res), ivox_coord(qy, m.inv_res), ivox_coord(qz, m.inv_res));
+    unsigned start, count;
+    if (!table_find(m.ctab, m.cmask, key, start, count)) return;
+    n_cand = count;
+    const float4* __restrict__ L = m.lists + start;
+    const float r2 = m.max_range2;
+    unsigned j = 0;
+#pragma unroll 1
+    for (; j + 4 <= count; j += 4) {
+        const float4 p0 = __ldg(L + j), p1 = __ldg(L + j + 1), p2 = __ldg(L + j + 2), p3 = __ldg(L + j + 3);
+        float e0 = dist2_ref(p0.x, p0.y, p0.z, qx, qy, qz);
+        float e1 = dist2_ref(p1.x, p1.y, p1.z, qx, qy, qz);
+        float e2 = dist2_ref(p2.x, p2.y, p2.z, qx, qy, qz);
+        float e3 = dist2_ref(p3.x, p3.y, p3.z, qx, qy, qz);
+        e0 = (e0 < r2) ? e0 : INFINITY;  // d < max_range^2 (voxel_grid_node.cpp:27 upstream)
+        e1 = (e1 < r2) ? e1 : INFINITY;
+        e2 = (e2 < r2) ? e2 : INFINITY;
+        e3 = (e3 < r2) ? e3 : INFINITY;
+        nn.push(e0, start + j);
+        nn.push(e1, start + j + 1);
+        nn.push(e2, start + j + 2);
+        nn.push(e3, start + j + 3);
+    }
+#pragma unroll 1
+    for (; j < count; ++j) {
+        const float4 p = __ldg(L + j);
+        float d = dist2_ref(p.x, p.y, p.z, qx, qy, qz);
+        d = (d < r2) ? d : INFINITY;
+        nn.push(d, start + j);
+    }
+}
+
+// ---- 5x3 least squares ---------------------------------------------------------------------------------------------
+// Householder reflection of column K (rows K..4) in the unnormalised form H = I - 2 v v^T / (v^T v), v = x - beta e_K:
+// the same reflector Eigen builds (loam_point_to_plane_ivox.h:283 -> colPivHouseholderQr), one sqrt + one division.
 template <int K>
 __device__ __forceinline__ void hh_step(double (&A)[5][3], double (&b)[5]) {
     const double alpha = A[K][K];
     double tail = 0;
 #pragma unroll
     for (int i = K + 1; i < 5; ++i) tail += A[i][K] * A[i][K];
-    if (tail == 0.0) return;  // tau = 0, beta = alpha: nothing to apply
+    if (tail == 0.0) return;  // already upper-triangular in this column
     double beta = sqrt(alpha * alpha + tail);
     if (alpha >= 0) beta = -beta;
-    const double inv = 1.0 / (alpha - beta);
-    const double tau = (beta - alpha) / beta;
     double v[5];
-    v[K] = 1.0;
+    v[K] = alpha - beta;
 #pragma unroll
-    for (int i = K + 1; i < 5; ++i) v[i] = A[i][K] * inv;
+    for (int i = K + 1; i < 5; ++i) v[i] = A[i][K];
+    const double f = 2.0 / (v[K] * v[K] + tail);
     A[K][K] = beta;
 #pragma unroll
     for (int j = K + 1; j < 3; ++j) {
         double s = 0;
 #pragma unroll
         for (int i = K; i < 5; ++i) s += v[i] * A[i][j];
-        s *= tau;
+        s *= f;
 #pragma unroll
         for (int i = K; i < 5; ++i) A[i][j] -= s * v[i];
     }
     double s = 0;
 #pragma unroll
     for (int i = K; i < 5; ++i) s += v[i] * b[i];
-    s *= tau;
+    s *= f;
 #pragma unroll
     for (int i = K; i < 5; ++i) b[i] -= s * v[i];
 }
@@ -82,15 +162,15 @@ __device__ __forceinline__ void swap_cols(double (&A)[5][3]) {
     }
 }
 
-// min || A c + 1 ||  — Eigen colPivHouseholderQr().solve(b) with b = -1 (loam_point_to_plane_ivox.h:275-283 upstream)
+// min || A c + 1 ||  — Eigen colPivHouseholderQr().solve(b) with b = -1 (loam_point_to_plane_ivox.h:275-283 upstream).
+// A is destroyed.
 __device__ __forceinline__ void plane_lstsq(double (&A)[5][3], double (&c)[3]) {
     double b[5] = {-1.0, -1.0, -1.0, -1.0, -1.0};
     int p0 = 0, p1 = 1, p2 = 2;
     int rank = 3;
     double n0 = colnorm2<0, 0>(A), n1 = colnorm2<0, 1>(A), n2 = colnorm2<0, 2>(A);
     const double maxcn = fmax(n0, fmax(n1, n2));
-    const double th = 2.220446049250313e-16 * sqrt(maxcn) / 5.0;
-    const double thr = th * th;
+    const double thr = maxcn * (2.220446049250313e-16 / 5.0) * (2.220446049250313e-16 / 5.0);
     {  // k = 0
         int piv = 0;
         double best = n0;
@@ -127,43 +207,85 @@ __device__ __forceinline__ void plane_lstsq(double (&A)[5][3], double (&c)[3]) {
     c[2] = (p0 == 2) ? y0 : ((p1 == 2) ? y1 : y2);
 }
 
+// Out-of-line QR path for ill-conditioned neighbourhoods (kept out of the hot path's register budget).
+__device__ __noinline__ void plane_lstsq_qr(const float4* __restrict__ lists, unsigned j0, unsigned j1, unsigned j2, unsigned j3, unsigned j4,
+                                            double (&c)[3]) {
+    const unsigned js[5] = {j0, j1, j2, j3, j4};
+    double A[5][3];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float4 a = __ldg(lists + js[i]);
+        A[i][0] = a.x; A[i][1] = a.y; A[i][2] = a.z;
+    }
+    plane_lstsq(A, c);
+}
+
 // Geometry of one source point against the map: returns true when the point produces a valid residual.
 __device__ __forceinline__ bool p2plane_point(const IvoxView& map, const float4 sp, const double* __restrict__ pose /*R[9], t[3]*/,
-                                              double plane_thres, double (&J)[6], double& ad, unsigned& n_cand) {
-    const double px = sp.x, py = sp.y, pz = sp.z;
-    const float qx = xform_row_d(pose[0], pose[1], pose[2], pose[9], px, py, pz);
-    const float qy = xform_row_d(pose[3], pose[4], pose[5], pose[10], px, py, pz);
-    const float qz = xform_row_d(pose[6], pose[7], pose[8], pose[11], px, py, pz);
-    Knn5 nn;
-    ivox_knn5_lists(map, qx, qy, qz, nn, n_cand);
+                                              double plane_thres, double (&J)[6], double& ad, unsigned& n_cand, unsigned& n_fallback) {
+    const float qx = xform_row_d(pose[0], pose[1], pose[2], pose[9], (double)sp.x, (double)sp.y, (double)sp.z);
+    const float qy = xform_row_d(pose[3], pose[4], pose[5], pose[10], (double)sp.x, (double)sp.y, (double)sp.z);
+    const float qz = xform_row_d(pose[6], pose[7], pose[8], pose[11], (double)sp.x, (double)sp.y, (double)sp.z);
+    Top5 nn;
+    knn5_stream(map, qx, qy, qz, nn, n_cand);
+    n_fallback = (unsigned)clock64();  // DEBUG: low 32 bits of the SM clock after the k-NN phase
     if (nn.j4 == 0xffffffffu) return false;  // fewer than 5 neighbours (:271-273)
-    double A[5][3];
-    {
-        const float4 a0 = __ldg(map.lists + nn.j0), a1 = __ldg(map.lists + nn.j1), a2 = __ldg(map.lists + nn.j2),
-                     a3 = __ldg(map.lists + nn.j3), a4 = __ldg(map.lists + nn.j4);
-        A[0][0] = a0.x; A[0][1] = a0.y; A[0][2] = a0.z;
-        A[1][0] = a1.x; A[1][1] = a1.y; A[1][2] = a1.z;
-        A[2][0] = a2.x; A[2][1] = a2.y; A[2][2] = a2.z;
-        A[3][0] = a3.x; A[3][1] = a3.y; A[3][2] = a3.z;
-        A[4][0] = a4.x; A[4][1] = a4.y; A[4][2] = a4.z;
-    }
-    const double a0x = A[0][0], a0y = A[0][1], a0z = A[0][2];
-    double Aq[5][3];
-#pragma unroll
-    for (int i = 0; i < 5; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) Aq[i][j] = A[i][j];
+    const unsigned js[5] = {nn.j0, nn.j1, nn.j2, nn.j3, nn.j4};
     double c[3];
-    plane_lstsq(Aq, c);
-    const double cn = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
-    bool valid = true;
+    {
+        // Fast path: normal equations (A^T A) c = -A^T 1 by a pivot-free LDL^T.  The inputs are fp32, so every product
+        // is exact in fp64 and each sum carries ~1e-16 relative error; the only loss is cancellation in the two Schur
+        // complements, which is measured — if either keeps fewer than ~9 digits the point takes the QR path below.
+        double sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0, bx = 0, by = 0, bz = 0;
 #pragma unroll
-    for (int j = 0; j < 5; ++j)
-        if (fabs(A[j][0] * c[0] + A[j][1] * c[1] + A[j][2] * c[2] + 1.0) / cn > plane_thres) valid = false;  // :286-293
+        for (int i = 0; i < 5; ++i) {
+            const float4 a = __ldg(map.lists + js[i]);
+            const double x = a.x, y = a.y, z = a.z;
+            sxx += x * x; sxy += x * y; sxz += x * z; syy += y * y; syz += y * z; szz += z * z;
+            bx -= x; by -= y; bz -= z;
+        }
+        bool ok = sxx > 0.0;
+        const double i0 = 1.0 / sxx;
+        const double l10 = sxy * i0, l20 = sxz * i0;
+        const double d1 = syy - l10 * sxy;
+        const double e = syz - l10 * sxz;
+        const double t2 = szz - l20 * sxz;
+        ok = ok && (d1 > 1e-7 * syy);
+        const double i1 = 1.0 / d1;
+        const double l21 = e * i1;
+        const double d2 = t2 - l21 * e;
+        ok = ok && (d2 > 1e-7 * fmax(szz, fabs(l21 * e)));
+        if (ok) {
+            const double y1 = by - l10 * bx;
+            const double y2 = bz - l20 * bx - l21 * y1;
+            const double c2 = y2 / d2;
+            const double c1 = y1 * i1 - l21 * c2;
+            c[0] = bx * i0 - l10 * c1 - l20 * c2;
+            c[1] = c1;
+            c[2] = c2;
+        } else {
+            ++n_fallback;
+            plane_lstsq_qr(map.lists, nn.j0, nn.j1, nn.j2, nn.j3, nn.j4, c);
+        }
+    }
+    const double cn = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    // |A_j c + 1| / ||c|| > thres  (:286-293), evaluated as |A_j c + 1| > thres * ||c||; the 5 rows are re-read
+    // (L1 hits) instead of being kept live across the QR
+    const double lim = plane_thres * cn;
+    bool valid = cn > 0.0;
+    float4 a0 = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float4 a = __ldg(map.lists + js[i]);
+        if (i == 0) a0 = a;
+        if (fabs((double)a.x * c[0] + (double)a.y * c[1] + (double)a.z * c[2] + 1.0) > lim) valid = false;
+    }
     if (!valid) return false;
-    const double nx = c[0] / cn, ny = c[1] / cn, nz = c[2] / cn;
-    const double d = ((double)qx - a0x) * nx + ((double)qy - a0y) * ny + ((double)qz - a0z) * nz;  // :306 from the nearest neighbour
-    if (sqrt(px * px + py * py + pz * pz) < 81.0 * d * d) return false;                              // :309 body-frame norm
+    const double icn = 1.0 / cn;
+    const double nx = c[0] * icn, ny = c[1] * icn, nz = c[2] * icn;
+    const double d = ((double)qx - (double)a0.x) * nx + ((double)qy - (double)a0.y) * ny + ((double)qz - (double)a0.z) * nz;  // :306
+    const double px = sp.x, py = sp.y, pz = sp.z;
+    if (sqrt(px * px + py * py + pz * pz) < 81.0 * d * d) return false;  // :309 body-frame norm
     const double s = d > 0 ? 1.0 : -1.0;
     const double rx = pose[0] * px + pose[1] * py + pose[2] * pz;
     const double ry = pose[3] * px + pose[4] * py + pose[5] * pz;
@@ -181,14 +303,20 @@ __device__ __forceinline__ bool p2plane_point(const IvoxView& map, const float4 
 // columns of the per-point staging record
 constexpr int kRecAd = 6, kRecValid = 7, kRecCand = 8, kRecHits = 9, kRecOne = 10, kRecW = 12;
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) p2plane_gn_kernel(P2PlaneLoopArgs a) {
-    cg::grid_group grid = cg::this_grid();
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs a) {
     constexpr int W = BLOCK / 32;
     __shared__ double s_pose[12];
     __shared__ double s_rec[W][32][kRecW];
     __shared__ double s_red[W][32];
+    __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_chunks = (a.n + 31) >> 5;              // warp-sized chunks
+    const int n_groups = ((int)gridDim.x + 31) >> 5;   // groups of 32 CTAs
+    const int n_warps = (int)gridDim.x * W;
+    double* __restrict__ rows = a.partials;                              // [gridDim.x][32]  one row per CTA
+    double* __restrict__ grows = a.partials + (size_t)gridDim.x * 32;    // [n_groups][32]
+    int* gcount = a.sync + 2 * a.gp.max_iterations + 1;                  // [n_groups], self-resetting
 
     // which product of record columns lane k accumulates: sum_k = sgn * sum_p rec[p][ca] * rec[p][cb]
     int ca = kRecOne, cb = kRecOne;
@@ -201,13 +329,13 @@ __global__ void __launch_bounds__(BLOCK) p2plane_gn_kernel(P2PlaneLoopArgs a) {
     } else if (lane < 27) {
         ca = lane - 21; cb = kRecAd; sgn = -1.0;  // g = sum -J |d|
     } else if (lane == kAccValid) {
-        ca = kRecValid; cb = kRecOne;
+        ca = kRecValid;
     } else if (lane == kAccRes) {
-        ca = kRecAd; cb = kRecOne;
+        ca = kRecAd;
     } else if (lane == kAccCand) {
-        ca = kRecCand; cb = kRecOne;
+        ca = kRecCand;
     } else if (lane == kAccHits) {
-        ca = kRecHits; cb = kRecOne;
+        ca = kRecHits;
     } else {
         sgn = 0.0;
     }
@@ -215,16 +343,20 @@ __global__ void __launch_bounds__(BLOCK) p2plane_gn_kernel(P2PlaneLoopArgs a) {
     for (int it = 0; it < a.gp.max_iterations; ++it) {
         if (threadIdx.x < 9) s_pose[threadIdx.x] = __ldcg(&a.state->R[threadIdx.x]);
         else if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(&a.state->t[threadIdx.x - 9]);
+        if (blockIdx.x == 0 && threadIdx.x == 0 && it < 16) a.state->dbg[it][0] = globaltimer_ns();
         __syncthreads();
+        if (a.dbg_cta && it == 1 && threadIdx.x == 0) a.dbg_cta[blockIdx.x * 4 + 0] = globaltimer_ns();
 
-        double acc = 0.0;
-        for (int base = blockIdx.x * BLOCK; base < a.n; base += gridDim.x * BLOCK) {
-            const int i = base + threadIdx.x;
+        double acc = 0.0;  // lane k's running sum over every chunk of this warp
+        // warp-granular work loop, static round-robin over 32-point chunks: no barrier, no atomics inside
+        for (int chunk = blockIdx.x * W + warp; chunk < n_chunks; chunk += n_warps) {
+            const int i = (chunk << 5) + lane;
             double J[6] = {0, 0, 0, 0, 0, 0}, ad = 0.0, vflag = 0.0;
-            unsigned n_cand = 0;
+            unsigned n_cand = 0, n_fb = 0;
+            const unsigned dbg_t0 = (unsigned)clock64();
             if (i < a.n) {
                 const float4 sp = a.src[i];
-                bool use = p2plane_point(a.map, sp, s_pose, a.plane_thres, J, ad, n_cand);
+                bool use = p2plane_point(a.map, sp, s_pose, a.plane_thres, J, ad, n_cand, n_fb);
                 if (use) {
                     a.rec0[i] = make_float4((float)J[0], (float)J[1], (float)J[2], (float)J[3]);
                     a.rec1[i] = make_float4((float)J[4], (float)J[5], (float)ad, 1.0f);
@@ -241,34 +373,77 @@ __global__ void __launch_bounds__(BLOCK) p2plane_gn_kernel(P2PlaneLoopArgs a) {
                 }
                 vflag = use ? 1.0 : 0.0;
             }
+            const unsigned dbg_t1 = (unsigned)clock64();
+            if (a.dbg_cta && it == 1) {  // DEBUG: per-warp phase cycles (max over lanes of k-NN phase, list length)
+                unsigned knn_c = (i < a.n && n_fb) ? (n_fb - dbg_t0) : 0u;
+                unsigned mx = n_cand, sm = n_cand;
+                for (int o = 16; o > 0; o >>= 1) {
+                    knn_c = max(knn_c, __shfl_xor_sync(0xffffffffu, knn_c, o));
+                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                }
+                if (lane == 0) {
+                    unsigned long long* w = a.dbg_cta + (size_t)gridDim.x * 4 + (size_t)(blockIdx.x * W + warp) * 4;
+                    w[0] = dbg_t1 - dbg_t0;
+                    w[1] = knn_c;
+                    w[2] = mx;
+                    w[3] = sm;
+                }
+            }
+            n_fb = 0;
             double* rec = s_rec[warp][lane];
 #pragma unroll
             for (int k = 0; k < 6; ++k) rec[k] = J[k];
             rec[kRecAd] = ad;
             rec[kRecValid] = vflag;
             rec[kRecCand] = (double)n_cand;
-            rec[kRecHits] = (n_cand > 0) ? 1.0 : 0.0;
+            rec[kRecHits] = (double)n_fb;  // points that took the QR path (diagnostic; reported as hits_total)
             rec[kRecOne] = 1.0;
             __syncwarp();
 #pragma unroll 8
             for (int p = 0; p < 32; ++p) acc += s_rec[warp][p][ca] * s_rec[warp][p][cb];
             __syncwarp();
         }
+        // ---- CTA row, then the last CTA of each group of 32 folds the group (fixed order at every level) ------------
+        if (a.dbg_cta && it == 1 && lane == 0) {
+            if (warp == 0) a.dbg_cta[blockIdx.x * 4 + 1] = globaltimer_ns();
+            if (warp == W - 1) a.dbg_cta[blockIdx.x * 4 + 2] = globaltimer_ns();
+        }
         s_red[warp][lane] = acc * sgn;
         __syncthreads();
-        if (threadIdx.x < kNumAcc) {
+        if (a.dbg_cta && it == 1 && threadIdx.x == 0) a.dbg_cta[blockIdx.x * 4 + 3] = globaltimer_ns();
+        if (warp == 0) {
             double v = 0;
 #pragma unroll
-            for (int w = 0; w < W; ++w) v += s_red[w][threadIdx.x];
-            a.partials[(size_t)blockIdx.x * kAccStride + threadIdx.x] = v;
+            for (int w = 0; w < W; ++w) v += s_red[w][lane];
+            rows[(size_t)blockIdx.x * 32 + lane] = v;
+            __threadfence();
+            const int g = blockIdx.x >> 5;
+            int done = 0;
+            if (lane == 0) done = atomicAdd(&gcount[g], 1);
+            done = __shfl_sync(0xffffffffu, done, 0);
+            const int gsize = min(32, (int)gridDim.x - (g << 5));
+            if (done == gsize - 1) {
+                __threadfence();
+                double u = 0;
+                const double* base = rows + ((size_t)g << 10) + lane;
+#pragma unroll 8
+                for (int r = 0; r < gsize; ++r) u += __ldcg(base + ((size_t)r << 5));
+                grows[(size_t)g * 32 + lane] = u;
+                if (lane == 0) gcount[g] = 0;  // ready for the next iteration (ordered by the hand-over below)
+            }
         }
+        // ---- iteration hand-over: the CTA that arrives last reduces, solves and releases the others ---------------
         __threadfence();
-        grid.sync();
-        if (blockIdx.x == 0) {
-            // fixed-order cross-block reduction: W groups of 32 lanes stride over the rows, then groups 0..W-1
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(&a.sync[2 * it + 1], 1) == (int)gridDim.x - 1) ? 1 : 0;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (threadIdx.x == 0 && it < 16) a.state->dbg[it][1] = globaltimer_ns();
             double v = 0;
-            if (lane < kNumAcc)
-                for (int b = warp; b < (int)gridDim.x; b += W) v += __ldcg(&a.partials[(size_t)b * kAccStride + lane]);
+#pragma unroll 4
+            for (int g = warp; g < n_groups; g += W) v += __ldcg(&grows[(size_t)g * 32 + lane]);  // fixed order
             s_red[warp][lane] = v;
             __syncthreads();
             if (warp == 0) {
@@ -279,18 +454,30 @@ __global__ void __launch_bounds__(BLOCK) p2plane_gn_kernel(P2PlaneLoopArgs a) {
                 s_red[0][lane] = t;
                 __syncwarp();
                 if (lane == 0) {
+                    if (it < 16) a.state->dbg[it][2] = globaltimer_ns();
                     gn_step(a.state, s_red[0], a.gp, a.log, a.log_cap);
+                    if (it < 16) a.state->dbg[it][3] = globaltimer_ns();
                     __threadfence();
+                    atomicExch(a.sync_flag, it + 1);  // release
                 }
             }
+        } else if (threadIdx.x == 0) {
+            // acquire: plain L2 loads with back-off — hundreds of CTAs poll this word while the stragglers still work,
+            // and atomics on one hot line would serialise in a single L2 slice and slow the whole memory system
+            unsigned ns = 128;
+            while (*reinterpret_cast<volatile int*>(a.sync_flag) < it + 1) {
+                __nanosleep(ns);
+                if (ns < 1024) ns <<= 1;
+            }
+            __threadfence();
         }
-        grid.sync();
+        __syncthreads();
         if (__ldcg(&a.state->done)) break;
     }
 }
 
 // ---- query ordering --------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned spread10(unsigned v) {
+__device__ __forceinline__ unsigned spread_bits3(unsigned v) {  // up to 10 bits -> every 3rd bit
     v &= 0x3ffu;
     v = (v | (v << 16)) & 0x030000ffu;
     v = (v | (v << 8)) & 0x0300f00fu;
@@ -299,8 +486,9 @@ __device__ __forceinline__ unsigned spread10(unsigned v) {
     return v;
 }
 
-// 30-bit Morton code of the query's voxel at the initial pose (low 10 bits per axis: the 512-voxel period exceeds
-// any scan's extent, and aliasing would only cost locality, never correctness)
+// 24-bit locality key of the query's voxel at the initial pose: 3-D Morton of the low 6 bits per axis (a 32 m cube,
+// the full height of a scan) topped with 3+3 more bits of x and y (256 m).  Wrap-around beyond that only costs
+// locality, never correctness.  24 bits = three 8-bit radix passes.
 __global__ void sortkey_kernel(const float4* __restrict__ src, int n, const GnState* __restrict__ state, float inv_res,
                                unsigned* __restrict__ keys, unsigned* __restrict__ idx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,8 +499,13 @@ __global__ void sortkey_kernel(const float4* __restrict__ src, int n, const GnSt
     const float qx = xform_row_d(R[0], R[1], R[2], t[0], sp.x, sp.y, sp.z);
     const float qy = xform_row_d(R[3], R[4], R[5], t[1], sp.x, sp.y, sp.z);
     const float qz = xform_row_d(R[6], R[7], R[8], t[2], sp.x, sp.y, sp.z);
-    keys[i] = spread10((unsigned)ivox_coord(qx, inv_res)) | (spread10((unsigned)ivox_coord(qy, inv_res)) << 1) |
-              (spread10((unsigned)ivox_coord(qz, inv_res)) << 2);
+    const unsigned kx = (unsigned)ivox_coord(qx, inv_res), ky = (unsigned)ivox_coord(qy, inv_res), kz = (unsigned)ivox_coord(qz, inv_res);
+    const unsigned lo = spread_bits3(kx & 63u) | (spread_bits3(ky & 63u) << 1) | (spread_bits3(kz & 63u) << 2);  // 18 bits
+    const unsigned hx = (kx >> 6) & 7u, hy = (ky >> 6) & 7u;
+    unsigned hi = 0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) hi |= (((hx >> b) & 1u) << (2 * b)) | (((hy >> b) & 1u) << (2 * b + 1));
+    keys[i] = lo | (hi << 18);
     idx[i] = (unsigned)i;
 }
 
@@ -325,9 +518,9 @@ __global__ void ivox_knn_test_kernel(IvoxView map, const float4* __restrict__ q,
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = q[i];
-    Knn5 nn;
+    Top5 nn;
     unsigned nc;
-    ivox_knn5_lists(map, p.x, p.y, p.z, nn, nc);
+    knn5_stream(map, p.x, p.y, p.z, nn, nc);
     const unsigned js[5] = {nn.j0, nn.j1, nn.j2, nn.j3, nn.j4};
     int f = 0;
     for (int k = 0; k < 5; ++k) {
@@ -341,6 +534,8 @@ __global__ void ivox_knn_test_kernel(IvoxView map, const float4* __restrict__ q,
     found[i] = f;
 }
 
+constexpr int kMinBlocks = 6;  // <= 80 registers: 24 warps / SM, enough resident warps to cover a 100k-point scan in one pass
+
 }  // namespace
 
 int p2plane_max_grid(int device) {
@@ -348,14 +543,22 @@ int p2plane_max_grid(int device) {
     if (device >= 0 && device < 64 && cached[device]) return cached[device];
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2plane_gn_kernel<kP2PlaneBlock>, kP2PlaneBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2plane_gn_kernel<kP2PlaneBlock, kMinBlocks>, kP2PlaneBlock, 0);
     const int g = sms * (per_sm > 0 ? per_sm : 1);
     if (device >= 0 && device < 64) cached[device] = g;
     return g;
 }
 
+int p2plane_chunks(int n) { return (n + 31) / 32; }
+// doubles needed by the partial-sum buffer: one 32-wide row per chunk + one per group of 32 chunks
+size_t p2plane_partials_len(int n) {
+    const size_t c = (size_t)p2plane_chunks(n);
+    return (c + (c + 31) / 32 + 2) * 32;
+}
+int p2plane_groups(int n) { return (p2plane_chunks(n) + 31) / 32; }
+
 int p2plane_grid(int n, int device) {
-    const int need = (n + kP2PlaneBlock - 1) / kP2PlaneBlock;
+    const int need = (p2plane_chunks(n) + (kP2PlaneBlock / 32) - 1) / (kP2PlaneBlock / 32);
     const int cap = p2plane_max_grid(device);
     const int g = need < cap ? need : cap;
     return g > 0 ? g : 1;
@@ -364,10 +567,11 @@ int p2plane_grid(int n, int device) {
 void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st) {
     P2PlaneLoopArgs args = a;
     void* params[] = {&args};
-    FLS_CUDA(cudaLaunchCooperativeKernel((const void*)p2plane_gn_kernel<kP2PlaneBlock>, dim3(grid), dim3(kP2PlaneBlock), params, 0, st));
+    FLS_CUDA(cudaLaunchCooperativeKernel((const void*)p2plane_gn_kernel<kP2PlaneBlock, kMinBlocks>, dim3(grid), dim3(kP2PlaneBlock), params, 0,
+                                         st));
 }
 
-// Morton-order the scan by the voxel each point falls into at the initial pose (state must be initialised).
+// Order the scan by the voxel each point falls into at the initial pose (state must be initialised).
 void sort_queries(const float4* d_src, int n, const GnState* d_state, float inv_res, float4* d_sorted, BuildScratch& sc, cudaStream_t st,
                   int* launches) {
     if (n <= 0) return;
@@ -377,10 +581,10 @@ void sort_queries(const float4* d_src, int n, const GnState* d_state, float inv_
     sc.idx_sorted.reserve(n);
     sortkey_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_src, n, d_state, inv_res, sc.k32a.p, sc.idx.p);
     size_t t1 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t1, sc.k32a.p, sc.k32b.p, sc.idx.p, sc.idx_sorted.p, n, 0, 30, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, sc.k32a.p, sc.k32b.p, sc.idx.p, sc.idx_sorted.p, n, 0, 24, st);
     sc.cub_tmp.reserve(t1 + 256);
     size_t tb = sc.cub_tmp.cap;
-    FLS_CUDA(cub::DeviceRadixSort::SortPairs(sc.cub_tmp.p, tb, sc.k32a.p, sc.k32b.p, sc.idx.p, sc.idx_sorted.p, n, 0, 30, st));
+    FLS_CUDA(cub::DeviceRadixSort::SortPairs(sc.cub_tmp.p, tb, sc.k32a.p, sc.k32b.p, sc.idx.p, sc.idx_sorted.p, n, 0, 24, st));
     gather4_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_src, sc.idx_sorted.p, n, d_sorted);
     if (launches) *launches += 6;
 }

@@ -1,0 +1,68 @@
+"""GPU parity: K4 LOAM feature extraction vs the CPU oracle — index lists identical, in emission order."""
+import numpy as np
+import pytest
+
+from funny_lidar_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(proj, corner_thr=1.0, planar_thr=0.1):
+    from funny_lidar_slam_b200.features import FeatureExtractor
+    from oracle import pyoracle as orc
+    n = len(proj["ordered"])
+    fx = FeatureExtractor(corner_thr, planar_thr)
+    gc, gp = fx.extract_indices(proj["depth"], proj["col"], n, proj["row_start"], proj["row_end"])
+    oc, op, _ = orc.extract_features(proj["depth"], proj["col"], n, proj["row_start"], proj["row_end"], corner_thr, planar_thr)
+    assert np.array_equal(gc, oc), (len(gc), len(oc))
+    assert np.array_equal(gp, op), (len(gp), len(op))
+    return gc, gp
+
+
+def test_spinning_64_line(world, traj):
+    proj = synth.make_projected_scan(world, traj[4], kind="spin", sensor="hdl64", seed=11)
+    gc, gp = _check(proj)
+    assert len(gc) > 100 and len(gp) > 50000
+
+
+def test_spinning_16_line_thresholds(world, traj):
+    proj = synth.make_projected_scan(world, traj[7], kind="spin", sensor="vlp16", seed=12)
+    for ct, pt in ((1.0, 0.1), (0.2, 0.05), (5.0, 1.0)):
+        _check(proj, ct, pt)
+
+
+def test_livox_shaped_config3(world, traj):
+    """BASELINE config 3: Livox-Avia-shaped 6 x 40000 organisation (~240k rays), thresholds 1.0 / 0.1."""
+    proj = synth.make_projected_scan(world, traj[2], kind="livox", seed=13)
+    gc, gp = _check(proj)
+    assert len(gp) > 100000
+
+
+def test_through_cluster_api(world, traj):
+    from funny_lidar_slam_b200.features import FeatureExtractor
+    from funny_lidar_slam_b200.registration import PointcloudCluster
+    proj = synth.make_projected_scan(world, traj[1], kind="spin", sensor="vlp16", seed=14)
+    cl = PointcloudCluster(ordered_cloud=proj["ordered"], point_depth_vec=proj["depth"], point_col_index_vec=proj["col"],
+                           row_start_index_vec=proj["row_start"], row_end_index_vec=proj["row_end"])
+    fx = FeatureExtractor(1.0, 0.1)
+    fx.ExtractFeatures(cl)
+    assert cl.corner_cloud.shape[1] == 4 and len(cl.planar_cloud) == len(fx.planar_idx)
+    assert np.array_equal(cl.corner_cloud, proj["ordered"][fx.corner_idx])
+
+
+def test_degenerate_rows():
+    """rows with fewer than 12 points are skipped (block_start >= block_end), empty input returns nothing."""
+    from funny_lidar_slam_b200.features import FeatureExtractor
+    from oracle import pyoracle as orc
+    rng = np.random.default_rng(5)
+    counts = [0, 7, 11, 12, 13, 40, 3, 200]
+    n = sum(counts)
+    depth = rng.uniform(3, 40, n).astype(np.float32)
+    col = np.concatenate([np.sort(rng.choice(1800, c, replace=False)) for c in counts]).astype(np.int32) if n else np.zeros(0, np.int32)
+    ends = np.cumsum(counts)
+    rs = (ends - np.array(counts) + 5).astype(np.int32)
+    re = (ends - 6).astype(np.int32)
+    fx = FeatureExtractor(1.0, 0.1)
+    gc, gp = fx.extract_indices(depth, col, n, rs, re)
+    oc, op, _ = orc.extract_features(depth, col, n, rs, re, 1.0, 0.1)
+    assert np.array_equal(gc, oc) and np.array_equal(gp, op)
