@@ -141,12 +141,14 @@ public:
         const int c[3] = {ci(q.x), ci(q.y), ci(q.z)};
         int maxshell = 0;
         for (int a = 0; a < 3; ++a) maxshell = std::max(maxshell, std::max(std::abs(c[a] - lo_[a]), std::abs(hi_[a] - c[a])));
+        bool done = false;
         for (int r = 0; r <= maxshell; ++r) {
             if (int(best.size()) == n) {
                 // every point in shell r is at least (r-1)*cell away along some axis
                 const float lb = float(r - 1) * cell_;
-                if (r >= 1 && lb > 0 && lb * lb > best.back().first) break;
+                if (r >= 1 && lb > 0 && lb * lb > best.back().first) { done = true; break; }
             }
+            if (r > 6) break;  // sparse / far query: shells grow as r^3 — finish by exhaustive scan below
             for (int dx = -r; dx <= r; ++dx)
                 for (int dy = -r; dy <= r; ++dy)
                     for (int dz = -r; dz <= r; ++dz) {
@@ -164,6 +166,18 @@ public:
                             }
                         }
                     }
+        }
+        if (!done && maxshell > 6) {  // exhaustive, exact by construction
+            best.clear();
+            for (size_t pi = 0; pi < pts_.size(); ++pi) {
+                std::pair<float, int> e{dist2f(pts_[pi], q), int(pi)};
+                if (int(best.size()) < n) {
+                    best.insert(std::upper_bound(best.begin(), best.end(), e), e);
+                } else if (e < best.back()) {
+                    best.pop_back();
+                    best.insert(std::upper_bound(best.begin(), best.end(), e), e);
+                }
+            }
         }
         for (int i = 0; i < n; ++i) { idx[i] = best[i].second; d2[i] = best[i].first; }
         return n;
