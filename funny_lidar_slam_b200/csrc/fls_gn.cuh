@@ -51,7 +51,8 @@ __device__ __forceinline__ void block_reduce_store(double (&acc)[kNumAcc], doubl
 // One Gauss-Newton step from the reduced totals `tot[kNumAcc]`: fills H/g, solves, updates the pose in `s`,
 // applies the plug-in's stop rule.  Executed by a single thread: every global read is issued up front (one L2
 // round trip instead of ~30 serialized ones), the arithmetic runs on locals, the results are stored at the end.
-__device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p, fls_iter_log* log, int log_cap) {
+__device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p, fls_iter_log* log, int log_cap, int* release_flag = nullptr,
+                               int release_value = 0) {
     double R[9], t[3];
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = __ldcg(&s->R[i]);
@@ -124,11 +125,16 @@ __device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p,
         }
         if (it + 1 >= p.max_iterations) stop = true;
     }
-    // ---- publish --------------------------------------------------------------------------------------------------
+    // ---- publish: what the other CTAs wait for goes out first (pose + done), then the hand-over flag, then the rest
 #pragma unroll
     for (int i = 0; i < 9; ++i) s->R[i] = R[i];
 #pragma unroll
     for (int i = 0; i < 3; ++i) s->t[i] = t[i];
+    if (stop) s->done = 1;
+    if (release_flag) {
+        __threadfence();
+        atomicExch(release_flag, release_value);
+    }
     s->last_rot = new_last_rot;
     s->last_pos = new_last_pos;
     for (int i = 0; i < 36; ++i) s->H[i] = H[i];
@@ -153,7 +159,6 @@ __device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p,
         L.sum_residual = sum_res;
         L.n_valid = n_valid;
     }
-    if (stop) s->done = 1;
 }
 #endif
 

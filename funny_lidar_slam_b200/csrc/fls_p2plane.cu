@@ -43,34 +43,25 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 // ---- branch-free top-5 ---------------------------------------------------------------------------------------------
+// Each entry is ONE 64-bit key {hi = IEEE bits of the fp32 squared distance, lo = candidate index} held in a double
+// register: for non-negative, non-NaN floats the bit pattern orders like the value, and positive doubles order like
+// their bit patterns, so fp64 min/max (one DMNMX each) is a compare-exchange on (distance, visit order) — the
+// ascending-index tie-break IS the reference's "earlier candidate wins" rule.  Rejected candidates carry the
+// sentinel key {+inf, 0xffffffff}, which never displaces anything.
 struct Top5 {
-    float d0, d1, d2, d3, d4;
-    unsigned j0, j1, j2, j3, j4;
-    __device__ __forceinline__ void init() {
-        d0 = d1 = d2 = d3 = d4 = INFINITY;
-        j0 = j1 = j2 = j3 = j4 = 0xffffffffu;
-    }
-#define FLS_CE(da, ja, db, jb)               \
-    {                                        \
-        const bool c_ = (db) < (da);         \
-        const float td_ = (da);              \
-        const unsigned tj_ = (ja);           \
-        (da) = c_ ? (db) : (da);             \
-        (ja) = c_ ? (jb) : (ja);             \
-        (db) = c_ ? td_ : (db);              \
-        (jb) = c_ ? tj_ : (jb);              \
-    }
-    // ascending (d, visit order): strict '<' everywhere, so a later candidate never passes an equal earlier one
+    double k0, k1, k2, k3, k4;
+    static __device__ __forceinline__ double make(float d, unsigned j) { return __hiloint2double(__float_as_int(d), (int)j); }
+    __device__ __forceinline__ void init() { k0 = k1 = k2 = k3 = k4 = make(INFINITY, 0xffffffffu); }
     __device__ __forceinline__ void push(float d, unsigned j) {
-        const bool c = d < d4;
-        d4 = c ? d : d4;
-        j4 = c ? j : j4;
-        FLS_CE(d3, j3, d4, j4)
-        FLS_CE(d2, j2, d3, j3)
-        FLS_CE(d1, j1, d2, j2)
-        FLS_CE(d0, j0, d1, j1)
+        k4 = fmin(k4, make(d, j));
+        double t;
+        t = fmin(k3, k4); k4 = fmax(k3, k4); k3 = t;
+        t = fmin(k2, k3); k3 = fmax(k2, k3); k2 = t;
+        t = fmin(k1, k2); k2 = fmax(k1, k2); k1 = t;
+        t = fmin(k0, k1); k1 = fmax(k0, k1); k0 = t;
     }
-#undef FLS_CE
+    __device__ __forceinline__ unsigned idx(double k) const { return (unsigned)__double2loint(k); }
+    __device__ __forceinline__ bool full() const { return idx(k4) != 0xffffffffu; }
 };
 
 // IVoxMap::GetClosestPoint through the stencil lists: one probe of the centre table, then a streaming scan of the
@@ -83,30 +74,37 @@ __device__ __forceinline__ void knn5_stream(const IvoxView& m, float qx, float q
     if (!table_find(m.ctab, m.cmask, key, start, count)) return;
     n_cand = count;
     const float4* __restrict__ L = m.lists + start;
+    // the run is contiguous: pull all of its cache lines into L1 at once (no registers held), so the dependent
+    // 4-wide batches below cost an L1 hit each instead of an L2/HBM round trip
+    {
+        const char* pb = reinterpret_cast<const char*>(L);
+        const unsigned bytes = count * 16u;
+#pragma unroll 1
+        for (unsigned o = 0; o < bytes; o += 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + o));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + bytes - 16u));
+    }
     const float r2 = m.max_range2;
     unsigned j = 0;
 #pragma unroll 1
     for (; j + 4 <= count; j += 4) {
         const float4 p0 = __ldg(L + j), p1 = __ldg(L + j + 1), p2 = __ldg(L + j + 2), p3 = __ldg(L + j + 3);
-        float e0 = dist2_ref(p0.x, p0.y, p0.z, qx, qy, qz);
-        float e1 = dist2_ref(p1.x, p1.y, p1.z, qx, qy, qz);
-        float e2 = dist2_ref(p2.x, p2.y, p2.z, qx, qy, qz);
-        float e3 = dist2_ref(p3.x, p3.y, p3.z, qx, qy, qz);
-        e0 = (e0 < r2) ? e0 : INFINITY;  // d < max_range^2 (voxel_grid_node.cpp:27 upstream)
-        e1 = (e1 < r2) ? e1 : INFINITY;
-        e2 = (e2 < r2) ? e2 : INFINITY;
-        e3 = (e3 < r2) ? e3 : INFINITY;
-        nn.push(e0, start + j);
-        nn.push(e1, start + j + 1);
-        nn.push(e2, start + j + 2);
-        nn.push(e3, start + j + 3);
+        const float e0 = dist2_ref(p0.x, p0.y, p0.z, qx, qy, qz);
+        const float e1 = dist2_ref(p1.x, p1.y, p1.z, qx, qy, qz);
+        const float e2 = dist2_ref(p2.x, p2.y, p2.z, qx, qy, qz);
+        const float e3 = dist2_ref(p3.x, p3.y, p3.z, qx, qy, qz);
+        // d < max_range^2 (voxel_grid_node.cpp:27 upstream); rejected candidates become the sentinel key
+        const bool i0 = e0 < r2, i1 = e1 < r2, i2 = e2 < r2, i3 = e3 < r2;
+        nn.push(i0 ? e0 : INFINITY, i0 ? start + j : 0xffffffffu);
+        nn.push(i1 ? e1 : INFINITY, i1 ? start + j + 1 : 0xffffffffu);
+        nn.push(i2 ? e2 : INFINITY, i2 ? start + j + 2 : 0xffffffffu);
+        nn.push(i3 ? e3 : INFINITY, i3 ? start + j + 3 : 0xffffffffu);
     }
 #pragma unroll 1
     for (; j < count; ++j) {
         const float4 p = __ldg(L + j);
-        float d = dist2_ref(p.x, p.y, p.z, qx, qy, qz);
-        d = (d < r2) ? d : INFINITY;
-        nn.push(d, start + j);
+        const float d = dist2_ref(p.x, p.y, p.z, qx, qy, qz);
+        const bool in = d < r2;
+        nn.push(in ? d : INFINITY, in ? start + j : 0xffffffffu);
     }
 }
 
@@ -229,8 +227,8 @@ __device__ __forceinline__ bool p2plane_point(const IvoxView& map, const float4 
     Top5 nn;
     knn5_stream(map, qx, qy, qz, nn, n_cand);
     n_fallback = (unsigned)clock64();  // DEBUG: low 32 bits of the SM clock after the k-NN phase
-    if (nn.j4 == 0xffffffffu) return false;  // fewer than 5 neighbours (:271-273)
-    const unsigned js[5] = {nn.j0, nn.j1, nn.j2, nn.j3, nn.j4};
+    if (!nn.full()) return false;  // fewer than 5 neighbours (:271-273)
+    const unsigned js[5] = {nn.idx(nn.k0), nn.idx(nn.k1), nn.idx(nn.k2), nn.idx(nn.k3), nn.idx(nn.k4)};
     double c[3];
     {
         // Fast path: normal equations (A^T A) c = -A^T 1 by a pivot-free LDL^T.  The inputs are fp32, so every product
@@ -265,7 +263,7 @@ __device__ __forceinline__ bool p2plane_point(const IvoxView& map, const float4 
             c[2] = c2;
         } else {
             ++n_fallback;
-            plane_lstsq_qr(map.lists, nn.j0, nn.j1, nn.j2, nn.j3, nn.j4, c);
+            plane_lstsq_qr(map.lists, js[0], js[1], js[2], js[3], js[4], c);
         }
     }
     const double cn = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
@@ -349,6 +347,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
 
         double acc = 0.0;  // lane k's running sum over every chunk of this warp
         // warp-granular work loop, static round-robin over 32-point chunks: no barrier, no atomics inside
+        // (consecutive chunks stay in one CTA: Morton neighbours share candidate lists in L1 — spreading them over SMs
+        //  for balance was measured 35 % slower)
         for (int chunk = blockIdx.x * W + warp; chunk < n_chunks; chunk += n_warps) {
             const int i = (chunk << 5) + lane;
             double J[6] = {0, 0, 0, 0, 0, 0}, ad = 0.0, vflag = 0.0;
@@ -455,20 +455,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
                 __syncwarp();
                 if (lane == 0) {
                     if (it < 16) a.state->dbg[it][2] = globaltimer_ns();
-                    gn_step(a.state, s_red[0], a.gp, a.log, a.log_cap);
+                    gn_step(a.state, s_red[0], a.gp, a.log, a.log_cap, a.sync_flag, it + 1);  // releases as soon as the pose is out
                     if (it < 16) a.state->dbg[it][3] = globaltimer_ns();
-                    __threadfence();
-                    atomicExch(a.sync_flag, it + 1);  // release
                 }
             }
         } else if (threadIdx.x == 0) {
             // acquire: plain L2 loads with back-off — hundreds of CTAs poll this word while the stragglers still work,
             // and atomics on one hot line would serialise in a single L2 slice and slow the whole memory system
-            unsigned ns = 128;
-            while (*reinterpret_cast<volatile int*>(a.sync_flag) < it + 1) {
-                __nanosleep(ns);
-                if (ns < 1024) ns <<= 1;
-            }
+            while (*reinterpret_cast<volatile int*>(a.sync_flag) < it + 1) __nanosleep(200);
             __threadfence();
         }
         __syncthreads();
@@ -521,7 +515,7 @@ __global__ void ivox_knn_test_kernel(IvoxView map, const float4* __restrict__ q,
     Top5 nn;
     unsigned nc;
     knn5_stream(map, p.x, p.y, p.z, nn, nc);
-    const unsigned js[5] = {nn.j0, nn.j1, nn.j2, nn.j3, nn.j4};
+    const unsigned js[5] = {nn.idx(nn.k0), nn.idx(nn.k1), nn.idx(nn.k2), nn.idx(nn.k3), nn.idx(nn.k4)};
     int f = 0;
     for (int k = 0; k < 5; ++k) {
         if (js[k] != 0xffffffffu) {
