@@ -185,8 +185,9 @@ int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* co
     a.sync_flag = sync_buf.p + 2 * (size_t)cfg.max_iterations;
     a.dbg_cta = nullptr;
     if (std::getenv("FLS_DEBUG_TIMING")) {
-        dbg_cta.reserve((size_t)grid * 4 * 5);
-        FLS_CUDA(cudaMemsetAsync(dbg_cta.p, 0, (size_t)grid * 4 * 5 * sizeof(unsigned long long), stream));
+        const size_t dbg_len = (size_t)grid * 4 * (1 + kP2PlaneBlock / 32);
+        dbg_cta.reserve(dbg_len);
+        FLS_CUDA(cudaMemsetAsync(dbg_cta.p, 0, dbg_len * sizeof(unsigned long long), stream));
         a.dbg_cta = dbg_cta.p;
         dbg_grid = grid;
     }
@@ -405,10 +406,10 @@ int Handle::finish_match(double* T, int* converged, fls_match_stats* st, long lo
     end_call(st);
     const GnState& s = *h_state;
     if (fused_loop && std::getenv("FLS_DEBUG_TIMING") && dbg_grid > 0 && s.iter > 1) {
-        std::vector<unsigned long long> h((size_t)dbg_grid * 4 * 5);
+        std::vector<unsigned long long> h((size_t)dbg_grid * 4 * (1 + kP2PlaneBlock / 32));
         cudaMemcpy(h.data(), dbg_cta.p, h.size() * 8, cudaMemcpyDeviceToHost);
         {
-            const int nw = dbg_grid * 4;
+            const int nw = dbg_grid * (kP2PlaneBlock / 32);
             std::vector<int> order(nw);
             for (int i = 0; i < nw; ++i) order[i] = i;
             const unsigned long long* w = h.data() + (size_t)dbg_grid * 4;

@@ -7,7 +7,7 @@
 
 namespace fls {
 
-static constexpr int kP2PlaneBlock = 128;
+static constexpr int kP2PlaneBlock = 384;  // 12 warps: consecutive chunks share L1, and the hand-over folds 3x fewer CTA rows
 static constexpr int kNdtBlock = 128;
 static constexpr int kIcpBlock = 128;
 

@@ -238,8 +238,10 @@ int IvoxMap::build_stencil_lists(cudaStream_t st) {
     sc.cub_tmp.reserve(t3 + 256);
     tb = sc.cub_tmp.cap;
     FLS_CUDA(cub::DeviceScan::ExclusiveSum(sc.cub_tmp.p, tb, ccount.p, cstart.p, nc, st));
+    // load factor <= 0.25: the centre table is probed once per point-iteration and a long linear-probing chain stalls
+    // a whole warp, so it is kept sparser than the occupied table
     size_t slots = 1024;
-    while (slots < 2 * (size_t)nc) slots <<= 1;
+    while (slots < 4 * (size_t)nc) slots <<= 1;
     ctab.reserve(slots);
     cmask = (unsigned)(slots - 1);
     lists.reserve(total);

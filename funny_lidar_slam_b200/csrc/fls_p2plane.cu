@@ -48,42 +48,48 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // their bit patterns, so fp64 min/max (one DMNMX each) is a compare-exchange on (distance, visit order) — the
 // ascending-index tie-break IS the reference's "earlier candidate wins" rule.  Rejected candidates carry the
 // sentinel key {+inf, 0xffffffff}, which never displaces anything.
+// (measured: holding {distance bits, index} as one fp64 key and using fmin/fmax compiles to DSETP + 2 FSEL per
+//  min/max on sm_100a — slower than the separate float / index compare-exchange below.)
 struct Top5 {
-    double k0, k1, k2, k3, k4;
-    static __device__ __forceinline__ double make(float d, unsigned j) { return __hiloint2double(__float_as_int(d), (int)j); }
-    __device__ __forceinline__ void init() { k0 = k1 = k2 = k3 = k4 = make(INFINITY, 0xffffffffu); }
-    __device__ __forceinline__ void push(float d, unsigned j) {
-        k4 = fmin(k4, make(d, j));
-        double t;
-        t = fmin(k3, k4); k4 = fmax(k3, k4); k3 = t;
-        t = fmin(k2, k3); k3 = fmax(k2, k3); k2 = t;
-        t = fmin(k1, k2); k2 = fmax(k1, k2); k1 = t;
-        t = fmin(k0, k1); k1 = fmax(k0, k1); k0 = t;
+    float d0, d1, d2, d3, d4;
+    unsigned k0, k1, k2, k3, k4;
+    __device__ __forceinline__ void init() {
+        d0 = d1 = d2 = d3 = d4 = INFINITY;
+        k0 = k1 = k2 = k3 = k4 = 0xffffffffu;
     }
-    __device__ __forceinline__ unsigned idx(double k) const { return (unsigned)__double2loint(k); }
-    __device__ __forceinline__ bool full() const { return idx(k4) != 0xffffffffu; }
+#define FLS_CE(da, ja, db, jb)               \
+    {                                        \
+        const bool c_ = (db) < (da);         \
+        const float td_ = (da);              \
+        const unsigned tj_ = (ja);           \
+        (da) = c_ ? (db) : (da);             \
+        (ja) = c_ ? (jb) : (ja);             \
+        (db) = c_ ? td_ : (db);              \
+        (jb) = c_ ? tj_ : (jb);              \
+    }
+    // ascending (d, visit order): strict '<' everywhere, so a later candidate never passes an equal earlier one;
+    // a rejected candidate arrives as {+inf, 0xffffffff} and never displaces anything
+    __device__ __forceinline__ void push(float d, unsigned j) {
+        const bool c = d < d4;
+        d4 = c ? d : d4;
+        k4 = c ? j : k4;
+        FLS_CE(d3, k3, d4, k4)
+        FLS_CE(d2, k2, d3, k3)
+        FLS_CE(d1, k1, d2, k2)
+        FLS_CE(d0, k0, d1, k1)
+    }
+#undef FLS_CE
+    __device__ __forceinline__ unsigned idx(unsigned k) const { return k; }
+    __device__ __forceinline__ bool full() const { return k4 != 0xffffffffu; }
 };
 
 // IVoxMap::GetClosestPoint through the stencil lists: one probe of the centre table, then a streaming scan of the
 // contiguous candidate run (already in the reference's visit order).  Indices refer to `lists`.
-__device__ __forceinline__ void knn5_stream(const IvoxView& m, float qx, float qy, float qz, Top5& nn, unsigned& n_cand) {
+// Exact scan with the full-precision (distance, visit order) comparator — the reference semantics.  Out of line: it is
+// the fallback of the quantised fast path below.
+__device__ __noinline__ void knn5_exact(const float4* __restrict__ L, unsigned start, unsigned count, float r2, float qx, float qy, float qz,
+                                        Top5& nn) {
     nn.init();
-    n_cand = 0;
-    const unsigned long long key = pack_key(ivox_coord(qx, m.inv_res), ivox_coord(qy, m.inv_res), ivox_coord(qz, m.inv_res));
-    unsigned start, count;
-    if (!table_find(m.ctab, m.cmask, key, start, count)) return;
-    n_cand = count;
-    const float4* __restrict__ L = m.lists + start;
-    // the run is contiguous: pull all of its cache lines into L1 at once (no registers held), so the dependent
-    // 4-wide batches below cost an L1 hit each instead of an L2/HBM round trip
-    {
-        const char* pb = reinterpret_cast<const char*>(L);
-        const unsigned bytes = count * 16u;
-#pragma unroll 1
-        for (unsigned o = 0; o < bytes; o += 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + o));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + bytes - 16u));
-    }
-    const float r2 = m.max_range2;
     unsigned j = 0;
 #pragma unroll 1
     for (; j + 4 <= count; j += 4) {
@@ -106,6 +112,83 @@ __device__ __forceinline__ void knn5_stream(const IvoxView& m, float qx, float q
         const bool in = d < r2;
         nn.push(in ? d : INFINITY, in ? start + j : 0xffffffffu);
     }
+}
+
+// Fast selection: six 32-bit keys {26 high bits of the fp32 squared distance | 6-bit position in the run}, ordered by
+// integer min/max (2 instructions per compare-exchange instead of 5).  Dropping the 6 low mantissa bits can only
+// mis-order candidates whose distances agree to 26 bits; that matters for the result only between ranks 1/2 (the
+// nearest neighbour anchors the point-to-plane distance) and 5/6 (membership of the 5-NN set) — exactly those two
+// pairs are checked afterwards and an ambiguous query (a few per 10 000) is re-run through knn5_exact.
+struct Top6q {
+    unsigned k0, k1, k2, k3, k4, k5;
+    __device__ __forceinline__ void init() { k0 = k1 = k2 = k3 = k4 = k5 = 0xffffffffu; }
+#define FLS_CEQ(a, b)                 \
+    {                                 \
+        const unsigned lo_ = min(a, b); \
+        b = max(a, b);                \
+        a = lo_;                      \
+    }
+    __device__ __forceinline__ void push(unsigned key) {
+        k5 = min(k5, key);
+        FLS_CEQ(k4, k5)
+        FLS_CEQ(k3, k4)
+        FLS_CEQ(k2, k3)
+        FLS_CEQ(k1, k2)
+        FLS_CEQ(k0, k1)
+    }
+#undef FLS_CEQ
+};
+
+__device__ __forceinline__ unsigned qkey(float d, float r2, unsigned jl) {
+    return (d < r2) ? ((__float_as_uint(d) & 0xffffffc0u) | jl) : 0xffffffffu;  // d < max_range^2 (voxel_grid_node.cpp:27 upstream)
+}
+
+// IVoxMap::GetClosestPoint through the stencil lists: one probe of the centre table, then a streaming scan of the
+// contiguous candidate run (already in the reference's visit order).  Indices refer to `lists`.
+__device__ __forceinline__ void knn5_stream(const IvoxView& m, float qx, float qy, float qz, Top5& nn, unsigned& n_cand) {
+    nn.init();
+    n_cand = 0;
+    const unsigned long long key = pack_key(ivox_coord(qx, m.inv_res), ivox_coord(qy, m.inv_res), ivox_coord(qz, m.inv_res));
+    unsigned start, count;
+    if (!table_find(m.ctab, m.cmask, key, start, count)) return;
+    n_cand = count;
+    const float4* __restrict__ L = m.lists + start;
+    const float r2 = m.max_range2;
+    if (count > 64u) {  // position does not fit the 6-bit field
+        knn5_exact(L, start, count, r2, qx, qy, qz, nn);
+        return;
+    }
+    Top6q t;
+    t.init();
+    unsigned j = 0;
+#pragma unroll 1
+    for (; j + 4 <= count; j += 4) {
+        const float4 p0 = __ldg(L + j), p1 = __ldg(L + j + 1), p2 = __ldg(L + j + 2), p3 = __ldg(L + j + 3);
+        const float e0 = dist2_ref(p0.x, p0.y, p0.z, qx, qy, qz);
+        const float e1 = dist2_ref(p1.x, p1.y, p1.z, qx, qy, qz);
+        const float e2 = dist2_ref(p2.x, p2.y, p2.z, qx, qy, qz);
+        const float e3 = dist2_ref(p3.x, p3.y, p3.z, qx, qy, qz);
+        t.push(qkey(e0, r2, j));
+        t.push(qkey(e1, r2, j + 1));
+        t.push(qkey(e2, r2, j + 2));
+        t.push(qkey(e3, r2, j + 3));
+    }
+#pragma unroll 1
+    for (; j < count; ++j) {
+        const float4 p = __ldg(L + j);
+        t.push(qkey(dist2_ref(p.x, p.y, p.z, qx, qy, qz), r2, j));
+    }
+    const bool amb = ((t.k0 >> 6) == (t.k1 >> 6) && t.k1 != 0xffffffffu) || ((t.k4 >> 6) == (t.k5 >> 6) && t.k5 != 0xffffffffu);
+    if (amb) {
+        knn5_exact(L, start, count, r2, qx, qy, qz, nn);
+        return;
+    }
+    // fewer than 5 in range leaves the tail at the sentinel ("not full")
+    nn.k0 = (t.k0 != 0xffffffffu) ? start + (t.k0 & 63u) : 0xffffffffu;
+    nn.k1 = (t.k1 != 0xffffffffu) ? start + (t.k1 & 63u) : 0xffffffffu;
+    nn.k2 = (t.k2 != 0xffffffffu) ? start + (t.k2 & 63u) : 0xffffffffu;
+    nn.k3 = (t.k3 != 0xffffffffu) ? start + (t.k3 & 63u) : 0xffffffffu;
+    nn.k4 = (t.k4 != 0xffffffffu) ? start + (t.k4 & 63u) : 0xffffffffu;
 }
 
 // ---- 5x3 least squares ---------------------------------------------------------------------------------------------
@@ -417,34 +500,30 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
 #pragma unroll
             for (int w = 0; w < W; ++w) v += s_red[w][lane];
             rows[(size_t)blockIdx.x * 32 + lane] = v;
+            // ---- iteration hand-over: ONE fence + ONE atomic per CTA; the CTA that arrives last folds every row
             __threadfence();
-            const int g = blockIdx.x >> 5;
-            int done = 0;
-            if (lane == 0) done = atomicAdd(&gcount[g], 1);
-            done = __shfl_sync(0xffffffffu, done, 0);
-            const int gsize = min(32, (int)gridDim.x - (g << 5));
-            if (done == gsize - 1) {
-                __threadfence();
-                double u = 0;
-                const double* base = rows + ((size_t)g << 10) + lane;
-#pragma unroll 8
-                for (int r = 0; r < gsize; ++r) u += __ldcg(base + ((size_t)r << 5));
-                grows[(size_t)g * 32 + lane] = u;
-                if (lane == 0) gcount[g] = 0;  // ready for the next iteration (ordered by the hand-over below)
-            }
+            int last = 0;
+            if (lane == 0) last = (atomicAdd(&a.sync[2 * it + 1], 1) == (int)gridDim.x - 1) ? 1 : 0;
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (lane == 0) s_last = last;
         }
-        // ---- iteration hand-over: the CTA that arrives last reduces, solves and releases the others ---------------
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) s_last = (atomicAdd(&a.sync[2 * it + 1], 1) == (int)gridDim.x - 1) ? 1 : 0;
         __syncthreads();
         if (s_last) {
             __threadfence();
             if (threadIdx.x == 0 && it < 16) a.state->dbg[it][1] = globaltimer_ns();
-            double v = 0;
-#pragma unroll 4
-            for (int g = warp; g < n_groups; g += W) v += __ldcg(&grows[(size_t)g * 32 + lane]);  // fixed order
-            s_red[warp][lane] = v;
+            // fixed-order fold of the gridDim.x CTA rows: warp w takes rows w, w+W, ...; 4 independent partial sums per
+            // lane keep ~4 x 32 loads in flight; (a0+a1)+(a2+a3), then warps 0..W-1
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            const int nrows = (int)gridDim.x;
+            int r = warp;
+            for (; r + 3 * W < nrows; r += 4 * W) {
+                a0 += __ldcg(&rows[(size_t)r * 32 + lane]);
+                a1 += __ldcg(&rows[(size_t)(r + W) * 32 + lane]);
+                a2 += __ldcg(&rows[(size_t)(r + 2 * W) * 32 + lane]);
+                a3 += __ldcg(&rows[(size_t)(r + 3 * W) * 32 + lane]);
+            }
+            for (; r < nrows; r += W) a0 += __ldcg(&rows[(size_t)r * 32 + lane]);
+            s_red[warp][lane] = (a0 + a1) + (a2 + a3);
             __syncthreads();
             if (warp == 0) {
                 double t = 0;
@@ -528,7 +607,7 @@ __global__ void ivox_knn_test_kernel(IvoxView map, const float4* __restrict__ q,
     found[i] = f;
 }
 
-constexpr int kMinBlocks = 6;  // <= 80 registers: 24 warps / SM, enough resident warps to cover a 100k-point scan in one pass
+constexpr int kMinBlocks = 2;  // 2 x 384 threads: <= 80 registers, 24 warps / SM — enough resident warps to cover a 100k-point scan in one pass
 
 }  // namespace
 
