@@ -156,21 +156,18 @@ int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* co
     if (ivox.n_pts == 0) return FLS_ERR_NO_MAP;
     const int ni = (int)n;
     const int grid = p2plane_grid(ni, cfg.device);
-    rec0.reserve(n);
-    rec1.reserve(n);
-    flags.reserve(n);
-    src_f.reserve(n);
+    rec0.reserve(n + 1);
+    rec1.reserve(n + 1);
+    flags.reserve(n + 1);
+    src_f.reserve(n + 1);
     partials.reserve(p2plane_partials_len(ni));
     // {next chunk, CTAs arrived} per iteration, the release flag, one self-resetting counter per chunk group
     const size_t n_sync = 2 * (size_t)cfg.max_iterations + 1 + (size_t)p2plane_groups(ni) + 1;
     sync_buf.reserve(n_sync);
-    FLS_CUDA(cudaMemsetAsync(sync_buf.p, 0, n_sync * sizeof(int), stream));
-    if (n) FLS_CUDA(cudaMemsetAsync(flags.p, 0, n, stream));
-    launch_gn_init(state.p, T, stream);
-    launches++;
-    // Morton-order the queries by the voxel they fall into at the initial pose (locality only: the sums are order-free
-    // up to fp64 rounding, and the persistent per-point records live in the same order for the whole Match)
-    sort_queries(d_src, ni, state.p, ivox.inv_res, src_f.p, scratch, stream, &launches);
+    // one prep kernel (state init, counter + flag reset, locality keys) + radix sort + gather: the queries end up in
+    // Morton order of the voxel they fall into at the initial pose (locality only: the sums are order-free up to fp64
+    // rounding, and the persistent per-point records live in the same order for the whole Match)
+    prepare_queries(d_src, ni, T, state.p, ivox.inv_res, flags.p, sync_buf.p, (int)n_sync, src_f.p, scratch, stream, &launches);
     P2PlaneLoopArgs a;
     a.src = src_f.p;
     a.n = ni;

@@ -34,8 +34,8 @@ int p2plane_chunks(int n);            // warp-sized (32-point) work chunks
 int p2plane_groups(int n);            // groups of 32 chunks
 size_t p2plane_partials_len(int n);   // doubles in the partial-sum buffer (chunk rows + group rows)
 void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st);
-void sort_queries(const float4* d_src, int n, const GnState* d_state, float inv_res, float4* d_sorted, BuildScratch& sc, cudaStream_t st,
-                  int* launches);
+void prepare_queries(const float4* d_src, int n, const double* T_colmajor, GnState* d_state, float inv_res, unsigned char* d_flags, int* d_sync,
+                     int n_sync, float4* d_sorted, BuildScratch& sc, cudaStream_t st, int* launches);
 void launch_ivox_knn_test(const IvoxView& map, const float4* d_q, int n, float4* d_out, int* d_found, cudaStream_t st);
 
 struct NdtArgs {

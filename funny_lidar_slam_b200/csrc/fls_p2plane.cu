@@ -432,6 +432,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
         // warp-granular work loop, static round-robin over 32-point chunks: no barrier, no atomics inside
         // (consecutive chunks stay in one CTA: Morton neighbours share candidate lists in L1 — spreading them over SMs
         //  for balance was measured 35 % slower)
+        // (dealing runs of 4 chunks round-robin over CTAs was also tried: slowest CTA 14.6 -> 13.4 us but median
+        //  9.5 -> 10.3 us, no net gain)
         for (int chunk = blockIdx.x * W + warp; chunk < n_chunks; chunk += n_warps) {
             const int i = (chunk << 5) + lane;
             double J[6] = {0, 0, 0, 0, 0, 0}, ad = 0.0, vflag = 0.0;
@@ -516,6 +518,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
             double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
             const int nrows = (int)gridDim.x;
             int r = warp;
+            for (; r + 7 * W < nrows; r += 8 * W) {  // 8 loads in flight per lane
+                const double v0 = __ldcg(&rows[(size_t)r * 32 + lane]), v1 = __ldcg(&rows[(size_t)(r + W) * 32 + lane]);
+                const double v2 = __ldcg(&rows[(size_t)(r + 2 * W) * 32 + lane]), v3 = __ldcg(&rows[(size_t)(r + 3 * W) * 32 + lane]);
+                const double v4 = __ldcg(&rows[(size_t)(r + 4 * W) * 32 + lane]), v5 = __ldcg(&rows[(size_t)(r + 5 * W) * 32 + lane]);
+                const double v6 = __ldcg(&rows[(size_t)(r + 6 * W) * 32 + lane]), v7 = __ldcg(&rows[(size_t)(r + 7 * W) * 32 + lane]);
+                a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+                a0 += v4; a1 += v5; a2 += v6; a3 += v7;
+            }
             for (; r + 3 * W < nrows; r += 4 * W) {
                 a0 += __ldcg(&rows[(size_t)r * 32 + lane]);
                 a1 += __ldcg(&rows[(size_t)(r + W) * 32 + lane]);
@@ -559,26 +569,49 @@ __device__ __forceinline__ unsigned spread_bits3(unsigned v) {  // up to 10 bits
     return v;
 }
 
-// 24-bit locality key of the query's voxel at the initial pose: 3-D Morton of the low 6 bits per axis (a 32 m cube,
-// the full height of a scan) topped with 3+3 more bits of x and y (256 m).  Wrap-around beyond that only costs
-// locality, never correctness.  24 bits = three 8-bit radix passes.
-__global__ void sortkey_kernel(const float4* __restrict__ src, int n, const GnState* __restrict__ state, float inv_res,
-                               unsigned* __restrict__ keys, unsigned* __restrict__ idx) {
+struct PoseArg {
+    double R[9];  // row-major
+    double t[3];
+};
+
+// Per-Match preparation in ONE launch: initialise the GN state from the caller's pose, clear the hand-over counters
+// and the per-point valid flags [quirk 1: reset once per Match], and compute the locality key of every query.
+// Key = 3-D Morton of the low 4 bits per axis of the query's voxel at the initial pose (an 8 m cube) topped with
+// `hbits` more bits each of x and y; wrap-around beyond that only costs locality, never correctness.
+// key_bits = 12 + 2*hbits: 24 bits = three 8-bit radix passes, 16 bits = two.
+__global__ void p2plane_prep_kernel(const float4* __restrict__ src, int n, PoseArg pose, float inv_res, int hbits, unsigned* __restrict__ keys,
+                                    unsigned* __restrict__ idx, unsigned char* __restrict__ flags, int* __restrict__ sync, int n_sync,
+                                    GnState* __restrict__ s) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0) {
+        for (int k = threadIdx.x; k < n_sync; k += blockDim.x) sync[k] = 0;
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < 9; ++k) s->R[k] = s->R0[k] = s->Rprev[k] = pose.R[k];
+            for (int k = 0; k < 3; ++k) s->t[k] = s->t0[k] = s->tprev[k] = pose.t[k];
+            s->last_rot = s->last_pos = 0.0;
+            s->sum_res = 0;
+            s->cand_total = s->hits_total = 0;
+            s->n_valid = 0;
+            s->iter = 0;
+            s->done = 0;
+            s->converged = 0;
+            s->failed = 0;
+        }
+    }
     if (i >= n) return;
+    flags[i] = 0;
     const float4 sp = src[i];
-    const double* R = state->R;
-    const double* t = state->t;
-    const float qx = xform_row_d(R[0], R[1], R[2], t[0], sp.x, sp.y, sp.z);
-    const float qy = xform_row_d(R[3], R[4], R[5], t[1], sp.x, sp.y, sp.z);
-    const float qz = xform_row_d(R[6], R[7], R[8], t[2], sp.x, sp.y, sp.z);
+    const double* R = pose.R;
+    const float qx = xform_row_d(R[0], R[1], R[2], pose.t[0], sp.x, sp.y, sp.z);
+    const float qy = xform_row_d(R[3], R[4], R[5], pose.t[1], sp.x, sp.y, sp.z);
+    const float qz = xform_row_d(R[6], R[7], R[8], pose.t[2], sp.x, sp.y, sp.z);
     const unsigned kx = (unsigned)ivox_coord(qx, inv_res), ky = (unsigned)ivox_coord(qy, inv_res), kz = (unsigned)ivox_coord(qz, inv_res);
-    const unsigned lo = spread_bits3(kx & 63u) | (spread_bits3(ky & 63u) << 1) | (spread_bits3(kz & 63u) << 2);  // 18 bits
-    const unsigned hx = (kx >> 6) & 7u, hy = (ky >> 6) & 7u;
+    const unsigned lo = spread_bits3(kx & 15u) | (spread_bits3(ky & 15u) << 1) | (spread_bits3(kz & 15u) << 2);  // 12 bits
+    const unsigned hm = (1u << hbits) - 1u;
+    const unsigned hx = (kx >> 4) & hm, hy = (ky >> 4) & hm;
     unsigned hi = 0;
-#pragma unroll
-    for (int b = 0; b < 3; ++b) hi |= (((hx >> b) & 1u) << (2 * b)) | (((hy >> b) & 1u) << (2 * b + 1));
-    keys[i] = lo | (hi << 18);
+    for (int b = 0; b < hbits; ++b) hi |= (((hx >> b) & 1u) << (2 * b)) | (((hy >> b) & 1u) << (2 * b + 1));
+    keys[i] = lo | (hi << 12);
     idx[i] = (unsigned)i;
 }
 
@@ -644,22 +677,37 @@ void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st) {
                                          st));
 }
 
-// Order the scan by the voxel each point falls into at the initial pose (state must be initialised).
-void sort_queries(const float4* d_src, int n, const GnState* d_state, float inv_res, float4* d_sorted, BuildScratch& sc, cudaStream_t st,
-                  int* launches) {
+// Per-Match preparation: state init + counter / flag reset + locality keys (one kernel), then order the scan by the
+// voxel each point falls into at the initial pose (CUB radix sort of {key, index}, gather).
+void prepare_queries(const float4* d_src, int n, const double* T_colmajor, GnState* d_state, float inv_res, unsigned char* d_flags, int* d_sync,
+                     int n_sync, float4* d_sorted, BuildScratch& sc, cudaStream_t st, int* launches) {
+    const int m = n > 0 ? n : 1;
+    sc.k32a.reserve(m);
+    sc.k32b.reserve(m);
+    sc.idx.reserve(m);
+    sc.idx_sorted.reserve(m);
+    PoseArg pose;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) pose.R[r * 3 + c] = T_colmajor[c * 4 + r];
+        pose.t[r] = T_colmajor[12 + r];
+    }
+    const char* kb = std::getenv("FLS_SORT_KEY_BITS");
+    // measured on B200 (tools/match_timing.py, 108 k points): 24-bit keys 186 us / Match, 16-bit keys 165 us — one
+    // 12 us onesweep pass less, and the fused kernel is no slower (22.9 vs 23.8 us / iteration): an 8 m x 32 m x 32 m
+    // Morton window is all the locality the L1 broadcast needs
+    int key_bits = kb ? std::atoi(kb) : 16;
+    if (key_bits != 16 && key_bits != 20 && key_bits != 24) key_bits = 16;
+    p2plane_prep_kernel<<<(m + 255) / 256, 256, 0, st>>>(d_src, n, pose, inv_res, (key_bits - 12) / 2, sc.k32a.p, sc.idx.p, d_flags, d_sync, n_sync,
+                                                        d_state);
+    if (launches) *launches += 1;
     if (n <= 0) return;
-    sc.k32a.reserve(n);
-    sc.k32b.reserve(n);
-    sc.idx.reserve(n);
-    sc.idx_sorted.reserve(n);
-    sortkey_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_src, n, d_state, inv_res, sc.k32a.p, sc.idx.p);
     size_t t1 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t1, sc.k32a.p, sc.k32b.p, sc.idx.p, sc.idx_sorted.p, n, 0, 24, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, sc.k32a.p, sc.k32b.p, sc.idx.p, sc.idx_sorted.p, n, 0, key_bits, st);
     sc.cub_tmp.reserve(t1 + 256);
     size_t tb = sc.cub_tmp.cap;
-    FLS_CUDA(cub::DeviceRadixSort::SortPairs(sc.cub_tmp.p, tb, sc.k32a.p, sc.k32b.p, sc.idx.p, sc.idx_sorted.p, n, 0, 24, st));
+    FLS_CUDA(cub::DeviceRadixSort::SortPairs(sc.cub_tmp.p, tb, sc.k32a.p, sc.k32b.p, sc.idx.p, sc.idx_sorted.p, n, 0, key_bits, st));
     gather4_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_src, sc.idx_sorted.p, n, d_sorted);
-    if (launches) *launches += 6;
+    if (launches) *launches += 2 + key_bits / 8 + 1;
 }
 
 void launch_ivox_knn_test(const IvoxView& map, const float4* d_q, int n, float4* d_out, int* d_found, cudaStream_t st) {
