@@ -122,6 +122,68 @@ def make_cfg(wl: dict, device: int, n_map: int, flags: int = 0):
     return _abi.default_config(wl["method"], device=device, ivox_capacity=max(1000000, 2 * n_map), flags=flags)
 
 
+def secondary_kernels(device: int, peak: float, log, steps: int = 6):
+    """Short measurements of the other §8 kernels (K2 NDT, K3 ICP, K4 features) beside the headline: scans/s with the
+    scan resident in HBM, live roofline of the residual kernel (CUDA events per launch), and the CPU oracle on the same
+    inputs.  Reduced scene (100 m world) so that the default bench run stays within minutes."""
+    import torch
+
+    from funny_lidar_slam_b200.features import FeatureExtractor
+    from funny_lidar_slam_b200.registration import Registration
+    from oracle import pyoracle as orc
+    out = {}
+    world = synth.make_world()
+    traj = synth.trajectory(16)
+    mp = synth.make_surface_map(world, spacing=0.3, seed=4321)
+    dev = torch.device("cuda", device)
+    for name, method, sensor, dpos, drot, extra in (
+            ("ndt_64line", _abi.FLS_NDT, "hdl64", 0.05, 0.5, dict(ndt_capacity=2000000)),
+            ("icp_16line", _abi.FLS_ICP_P2P, "vlp16", 0.3, 3.0, {})):
+        scans = [synth.make_scan(world, traj[3 + 2 * i], sensor, seed=300 + i)["points"] for i in range(3)]
+        guesses = [synth.perturb_pose(traj[3 + 2 * i], seed=900 + i, dpos=dpos, drot_deg=drot) for i in range(3)]
+        cfg = _abi.default_config(method, device=device, flags=_abi.FLS_FLAG_PROFILE, **extra)
+        reg = Registration(cfg)
+        reg.AddCloudToLocalMap([mp])
+        d_scans = [torch.from_numpy(s).to(dev) for s in scans]
+        for i in range(3):
+            reg.match_device(d_scans[i].data_ptr(), len(scans[i]), guesses[i].copy())
+        ms = k_ms = 0.0
+        k_n = k_b = its = nsrc = 0
+        for i in range(steps):
+            reg.match_device(d_scans[i % 3].data_ptr(), len(scans[i % 3]), guesses[i % 3].copy())
+            st = reg.last_stats
+            ms += st.gpu_ms
+            k_ms += st.kernel_ms
+            k_n += st.kernel_launches
+            k_b += st.algo_bytes
+            its += st.iterations
+            nsrc += st.n_source
+        oreg = orc.Registration(_abi.default_config(method, **extra))
+        oreg.add_cloud(mp)
+        t_cpu = 0.0
+        for i in range(3):
+            oreg.match(scans[i], guesses[i])
+            t_cpu += oreg.last_seconds
+        ach = (k_b / max(k_ms, 1e-9)) / 1e6  # bytes/ms -> GB/s
+        out[name] = {"scans_per_s_gpu_span": steps / (ms * 1e-3), "mean_gn_iters": its / steps, "points_in_gn_loop": nsrc // steps,
+                     "kernel_avg_us": 1e3 * k_ms / max(k_n, 1), "roofline_achieved_gbs": ach, "roofline_frac": ach / peak,
+                     "cpu_oracle_scans_per_s": 3 / t_cpu, "cpu_threads": orc.num_threads(), "map_points": int(len(mp)), "l2": "warm"}
+        log(f"secondary {name}: {out[name]}")
+    proj = synth.make_projected_scan(world, traj[2], kind="livox", seed=13, samples=65000)
+    n = len(proj["ordered"])
+    fx = FeatureExtractor(1.0, 0.1, device=device)
+    for _ in range(2):
+        fx.extract_indices(proj["depth"], proj["col"], n, proj["row_start"], proj["row_end"])
+    g_ms = 0.0
+    for _ in range(steps):
+        fx.extract_indices(proj["depth"], proj["col"], n, proj["row_start"], proj["row_end"])
+        g_ms += fx.last_stats.gpu_ms
+    _, _, sec = orc.extract_features(proj["depth"], proj["col"], n, proj["row_start"], proj["row_end"], 1.0, 0.1)
+    out["features_livox_shaped"] = {"points": n, "rows": int(proj["rows"]), "gpu_ms_incl_h2d_d2h": g_ms / steps, "cpu_oracle_ms_1thread": sec * 1e3,
+                                    "algo_gbs": n * 50 / (g_ms / steps * 1e-3) / 1e9}
+    return out
+
+
 def run_reference(args, wl, log):
     """--impl reference: the CPU oracle on all host cores, same config/metric; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -163,6 +225,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short K2/K3/K4 side measurements")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -310,6 +373,13 @@ def main():
         cpu = {"value": n_cpu / t_cpu, "unit": "scans/s", "cores": orc.num_threads(), "kind": "port",
                "sample": f"{n_cpu} Match calls ({t_cpu:.1f}s) of the CPU oracle on the same scans/map, OpenMP on all host threads, "
                          "reference unbuildable here (no Eigen/PCL/TBB)"}
+        del oreg
+    other = None
+    if rank == 0 and world_size == 1 and not args.no_secondary:
+        try:
+            other = secondary_kernels(local_rank, peak, log)
+        except Exception as e:  # the headline line must not depend on the side measurements
+            other = {"error": repr(e)}
 
     if rank == 0:
         pos = float(np.median([e[0] for e in errs]))
@@ -331,6 +401,7 @@ def main():
                          "launches": int(k_launch), "avg_launch_us": 1e3 * k_ms / max(k_launch, 1), "algo_bytes_per_launch": k_bytes / max(k_launch, 1)},
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "other_kernels": other,
         }
         print(json.dumps(out), flush=True)
     if world_size > 1:
