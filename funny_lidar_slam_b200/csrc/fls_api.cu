@@ -121,23 +121,25 @@ void Handle::set_fit_cloud(const float4* d, size_t n) {
     fit_cloud_version++;
 }
 
-// ---- generic device-resident GN loop ---------------------------------------------------------------------------
-template <typename Launch>
-static void gn_loop(Handle& h, int method, int grid, int min_effective, Launch&& launch_residual) {
-    GnParams gp;
-    gp.method = method;
-    gp.max_iterations = h.cfg.max_iterations;
-    gp.min_effective = min_effective;
-    gp.n_blocks = grid;
-    gp.rot_thres = h.cfg.rotation_converge_thres;
-    gp.pos_thres = h.cfg.position_converge_thres;
-    for (int it = 0; it < h.cfg.max_iterations; ++it) {
-        if (h.profile) FLS_CUDA(cudaEventRecord(h.prof_ev[2 * it], h.stream));
-        launch_residual();
-        if (h.profile) FLS_CUDA(cudaEventRecord(h.prof_ev[2 * it + 1], h.stream));
-        launch_gn_solve(h.state.p, h.partials.p, gp, h.log.p, h.log_cap, h.stream);
-        h.launches += (grid > 0 ? 2 : 1);
-    }
+// ---- control block of a persistent GN loop (K2 / K3): rows + hand-over counters + stop rule ------------------------
+static GnLoopCtl make_ctl(Handle& h, int method, int grid, int min_effective) {
+    const size_t n_sync = 2 * (size_t)h.cfg.max_iterations + 2;
+    h.sync_buf.reserve(n_sync);
+    h.partials.reserve((size_t)(grid + 1) * 32);
+    GnLoopCtl c;
+    c.state = h.state.p;
+    c.rows = h.partials.p;
+    c.sync = h.sync_buf.p;
+    c.sync_flag = h.sync_buf.p + 2 * (size_t)h.cfg.max_iterations;
+    c.gp.method = method;
+    c.gp.max_iterations = h.cfg.max_iterations;
+    c.gp.min_effective = min_effective;
+    c.gp.n_blocks = grid;
+    c.gp.rot_thres = h.cfg.rotation_converge_thres;
+    c.gp.pos_thres = h.cfg.position_converge_thres;
+    c.log = h.log.p;
+    c.log_cap = h.log_cap;
+    return c;
 }
 
 // ---- LoamPointToPlaneIVOX ------------------------------------------------------------------------------------
@@ -230,11 +232,11 @@ int Handle::match_ndt(const float4* d_in, size_t n_in, double* T, int* converged
     src_f.reserve(n_in);
     const size_t n = voxel_grid_device(d_in, n_in, cfg.source_cloud_filter_size, src_f.p, scratch, stream, &launches);  // :232
     const int ni = (int)n;
-    const int grid = ndt_grid(ni);
-    partials.reserve((size_t)(grid > 0 ? grid : 1) * kAccStride);
+    const int grid = ndt_grid(ni, cfg.device);
+    GnLoopCtl ctl = make_ctl(*this, FLS_NDT, grid, cfg.ndt_min_effective_pts);
     double T_in[16];
     std::memcpy(T_in, T, sizeof(T_in));
-    launch_gn_init(state.p, T, stream);
+    launch_gn_init(state.p, T, stream, sync_buf.p, 2 * cfg.max_iterations + 2);
     launches++;
     NdtArgs a;
     a.src = src_f.p;
@@ -248,7 +250,11 @@ int Handle::match_ndt(const float4* d_in, size_t n_in, double* T, int* converged
     per_point_iter_bytes = 16 + 16LL * 7;
     per_cand_bytes = 80;
     per_hit_bytes = 0;
-    gn_loop(*this, FLS_NDT, grid, cfg.ndt_min_effective_pts, [&] { launch_ndt_iter(a, stream); });
+    if (profile) FLS_CUDA(cudaEventRecord(prof_ev[0], stream));
+    launch_ndt_loop(a, ctl, grid, stream);
+    if (profile) FLS_CUDA(cudaEventRecord(prof_ev[1], stream));
+    launches++;
+    fused_loop = true;
     last_src = src_f.p;
     last_src_n = n;
     const int rc = finish_match(T, converged, st, (long long)n);
@@ -313,9 +319,9 @@ int Handle::match_icp(const float4* d_in, size_t n_in, double* T, int* converged
     src_f.reserve(n_in);
     const size_t n = voxel_grid_device(d_in, n_in, cfg.source_cloud_filter_size, src_f.p, scratch, stream, &launches);  // :57
     const int ni = (int)n;
-    const int grid = icp_grid_blocks(ni);
-    partials.reserve((size_t)(grid > 0 ? grid : 1) * kAccStride);
-    launch_gn_init(state.p, T, stream);
+    const int grid = icp_grid_blocks(ni, cfg.device);
+    GnLoopCtl ctl = make_ctl(*this, FLS_ICP_P2P, grid, 0);
+    launch_gn_init(state.p, T, stream, sync_buf.p, 2 * cfg.max_iterations + 2);
     launches++;
     IcpArgs a;
     a.src = src_f.p;
@@ -328,7 +334,11 @@ int Handle::match_icp(const float4* d_in, size_t n_in, double* T, int* converged
     per_point_iter_bytes = 16 + 16LL * 27;
     per_cand_bytes = 16;
     per_hit_bytes = 0;
-    gn_loop(*this, FLS_ICP_P2P, grid, 0, [&] { launch_icp_iter(a, stream); });
+    if (profile) FLS_CUDA(cudaEventRecord(prof_ev[0], stream));
+    launch_icp_loop(a, ctl, grid, stream);
+    if (profile) FLS_CUDA(cudaEventRecord(prof_ev[1], stream));
+    launches++;
+    fused_loop = true;
     last_src = src_f.p;
     last_src_n = n;
     const int rc = finish_match(T, converged, st, (long long)n);

@@ -7,7 +7,8 @@ namespace fls {
 namespace {
 
 __global__ void gn_init_kernel(GnState* s, double t00, double t10, double t20, double t01, double t11, double t21, double t02, double t12,
-                               double t22, double t03, double t13, double t23) {
+                               double t22, double t03, double t13, double t23, int* sync, int n_sync) {
+    for (int k = threadIdx.x; k < n_sync; k += blockDim.x) sync[k] = 0;
     if (threadIdx.x != 0) return;
     // arguments are the column-major Mat4d entries T(r,c) named t<r><c>
     const double R[9] = {t00, t01, t02, t10, t11, t12, t20, t21, t22};
@@ -42,9 +43,9 @@ __global__ void __launch_bounds__(32) gn_solve_kernel(GnState* s, const double* 
 
 }  // namespace
 
-void launch_gn_init(GnState* d_state, const double* T, cudaStream_t st) {
+void launch_gn_init(GnState* d_state, const double* T, cudaStream_t st, int* d_sync, int n_sync) {
     // T is column-major: T[c*4 + r]
-    gn_init_kernel<<<1, 32, 0, st>>>(d_state, T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10], T[12], T[13], T[14]);
+    gn_init_kernel<<<1, 128, 0, st>>>(d_state, T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10], T[12], T[13], T[14], d_sync, n_sync);
 }
 
 void launch_gn_solve(GnState* d_state, const double* d_partials, const GnParams& p, fls_iter_log* d_log, int log_capacity, cudaStream_t st) {

@@ -21,7 +21,19 @@ struct GnParams {
     double rot_thres, pos_thres;
 };
 
-void launch_gn_init(GnState* d_state, const double* T_colmajor, cudaStream_t st);
+// Control block of a persistent (one launch per Match) Gauss-Newton loop
+struct GnLoopCtl {
+    GnState* state;
+    double* rows;    // [gridDim.x][32] per-CTA partial sums
+    int* sync;       // [2*max_iterations]: slot 2*it+1 counts the CTAs that finished iteration `it`
+    int* sync_flag;  // iterations completed (release flag)
+    GnParams gp;
+    fls_iter_log* log;
+    int log_cap;
+};
+
+// state initialisation (+ optional zeroing of the hand-over counters) in one launch
+void launch_gn_init(GnState* d_state, const double* T_colmajor, cudaStream_t st, int* d_sync = nullptr, int n_sync = 0);
 void launch_gn_solve(GnState* d_state, const double* d_partials, const GnParams& p, fls_iter_log* d_log, int log_capacity, cudaStream_t st);
 
 #ifdef __CUDACC__
@@ -159,6 +171,69 @@ __device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p,
         L.sum_residual = sum_res;
         L.n_valid = n_valid;
     }
+}
+
+// Tail of one iteration of a persistent GN loop (all threads of all CTAs call it with their per-thread sums):
+// block reduction -> CTA row -> ONE fence + ONE atomic per CTA -> the CTA that arrives last folds every row in a fixed
+// order, runs gn_step (which publishes the pose and releases the flag) -> everybody else waits on the flag.
+// Needs co-resident CTAs (cooperative launch).  Returns true when the loop is finished.
+template <int BLOCK>
+__device__ __forceinline__ bool gn_handover(double (&acc)[kNumAcc], const GnLoopCtl& c, int it) {
+    constexpr int W = BLOCK / 32;
+    __shared__ double s_red[W][kAccStride];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kNumAcc; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[warp][k] = v;
+    }
+    if (lane == 0) s_red[warp][kNumAcc] = 0.0;
+    __syncthreads();
+    if (warp == 0) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) v += s_red[w][lane];
+        c.rows[(size_t)blockIdx.x * 32 + lane] = v;
+        __threadfence();
+        int last = 0;
+        if (lane == 0) last = (atomicAdd(&c.sync[2 * it + 1], 1) == (int)gridDim.x - 1) ? 1 : 0;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (lane == 0) s_last = last;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        const int nrows = (int)gridDim.x;
+        int r = warp;
+        for (; r + 3 * W < nrows; r += 4 * W) {
+            a0 += __ldcg(&c.rows[(size_t)r * 32 + lane]);
+            a1 += __ldcg(&c.rows[(size_t)(r + W) * 32 + lane]);
+            a2 += __ldcg(&c.rows[(size_t)(r + 2 * W) * 32 + lane]);
+            a3 += __ldcg(&c.rows[(size_t)(r + 3 * W) * 32 + lane]);
+        }
+        for (; r < nrows; r += W) a0 += __ldcg(&c.rows[(size_t)r * 32 + lane]);
+        __syncthreads();  // everyone is done reading s_red from the block reduction
+        s_red[warp][lane] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        if (warp == 0) {
+            double t = 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) t += s_red[w][lane];
+            __syncwarp();
+            s_red[0][lane] = t;
+            __syncwarp();
+            if (lane == 0) gn_step(c.state, s_red[0], c.gp, c.log, c.log_cap, c.sync_flag, it + 1);
+        }
+    } else if (threadIdx.x == 0) {
+        while (*reinterpret_cast<volatile int*>(c.sync_flag) < it + 1) __nanosleep(200);
+        __threadfence();
+    }
+    __syncthreads();
+    return __ldcg(&c.state->done) != 0;
 }
 #endif
 

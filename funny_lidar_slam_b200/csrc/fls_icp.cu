@@ -48,13 +48,14 @@ __device__ __forceinline__ bool grid_nn1(const IvoxView& g, float qx, float qy, 
     return best_j != 0xffffffffu;
 }
 
+// One persistent launch runs every Gauss-Newton iteration of a Match (gn_handover, fls_gn.cuh).
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) icp_iter_kernel(IcpArgs a) {
+__global__ void __launch_bounds__(BLOCK) icp_gn_kernel(IcpArgs a, GnLoopCtl ctl) {
     __shared__ double s_pose[12];
     __shared__ float s_posef[12];
-    if (a.state->done) return;
+    for (int it = 0; it < ctl.gp.max_iterations; ++it) {
     if (threadIdx.x < 12) {
-        const double v = threadIdx.x < 9 ? a.state->R[threadIdx.x] : a.state->t[threadIdx.x - 9];
+        const double v = threadIdx.x < 9 ? __ldcg(&a.state->R[threadIdx.x]) : __ldcg(&a.state->t[threadIdx.x - 9]);
         s_pose[threadIdx.x] = v;
         s_posef[threadIdx.x] = (float)v;  // R.cast<float>(), t.cast<float>()  (pointcloud_utility.h:145-146)
     }
@@ -63,8 +64,7 @@ __global__ void __launch_bounds__(BLOCK) icp_iter_kernel(IcpArgs a) {
 #pragma unroll
     for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.0;
 
-    const int i = blockIdx.x * BLOCK + threadIdx.x;
-    if (i < a.n) {
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < a.n; i += gridDim.x * BLOCK) {
         const float4 sp = a.src[i];
         const float qx = xform_row_f(s_posef[0], s_posef[1], s_posef[2], s_posef[9], sp.x, sp.y, sp.z);
         const float qy = xform_row_f(s_posef[3], s_posef[4], s_posef[5], s_posef[10], sp.x, sp.y, sp.z);
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(BLOCK) icp_iter_kernel(IcpArgs a) {
         float d2;
         unsigned j, nc, nh;
         const bool found = grid_nn1(a.map, qx, qy, qz, d2, j, nc, nh);
-        acc[kAccCand] = (double)nc;
-        acc[kAccHits] = (double)nh;
+        acc[kAccCand] += (double)nc;
+        acc[kAccHits] += (double)nh;
         if (found && !((double)d2 > a.max_corr)) {  // icp_optimized.h:87
             const float4 m = __ldg(a.map.pts + j);
             const double e0 = (double)qx - (double)m.x, e1 = (double)qy - (double)m.y, e2 = (double)qz - (double)m.z;
@@ -88,23 +88,24 @@ __global__ void __launch_bounds__(BLOCK) icp_iter_kernel(IcpArgs a) {
                 A[r][2] = -(r0 * py - r1 * px);
             }
             // dx = [dt(0..2), dθ(3..5)]:  H = [[I, A],[A^T, A^T A]],  b = -[e ; A^T e]
-            acc[tri6(0, 0)] = 1.0; acc[tri6(1, 1)] = 1.0; acc[tri6(2, 2)] = 1.0;
+            acc[tri6(0, 0)] += 1.0; acc[tri6(1, 1)] += 1.0; acc[tri6(2, 2)] += 1.0;
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) acc[tri6(r, 3 + c)] = A[r][c];
+                for (int c = 0; c < 3; ++c) acc[tri6(r, 3 + c)] += A[r][c];
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int c = r; c < 3; ++c) acc[tri6(3 + r, 3 + c)] = A[0][r] * A[0][c] + A[1][r] * A[1][c] + A[2][r] * A[2][c];
-            acc[21] = -e0; acc[22] = -e1; acc[23] = -e2;
+                for (int c = r; c < 3; ++c) acc[tri6(3 + r, 3 + c)] += A[0][r] * A[0][c] + A[1][r] * A[1][c] + A[2][r] * A[2][c];
+            acc[21] -= e0; acc[22] -= e1; acc[23] -= e2;
 #pragma unroll
-            for (int r = 0; r < 3; ++r) acc[24 + r] = -(A[0][r] * e0 + A[1][r] * e1 + A[2][r] * e2);
-            acc[kAccValid] = 1.0;
-            acc[kAccRes] = sqrt(e0 * e0 + e1 * e1 + e2 * e2);  // total_res += error.norm()  (:126)
+            for (int r = 0; r < 3; ++r) acc[24 + r] -= (A[0][r] * e0 + A[1][r] * e1 + A[2][r] * e2);
+            acc[kAccValid] += 1.0;
+            acc[kAccRes] += sqrt(e0 * e0 + e1 * e1 + e2 * e2);  // total_res += error.norm()  (:126)
         }
     }
-    block_reduce_store<BLOCK>(acc, a.partials + (size_t)blockIdx.x * kAccStride);
+    if (gn_handover<BLOCK>(acc, ctl, it)) break;
+    }
 }
 
 // GetFitnessScore (icp_optimized.h:191-215 upstream): mean squared 1-NN distance over points with d2 <= max_range
@@ -147,10 +148,24 @@ __global__ void fitness_kernel(IvoxView g, const float4* __restrict__ src, int n
 
 }  // namespace
 
-int icp_grid_blocks(int n) { return (n + kIcpBlock - 1) / kIcpBlock; }
-void launch_icp_iter(const IcpArgs& a, cudaStream_t st) {
-    if (a.n <= 0) return;
-    icp_iter_kernel<kIcpBlock><<<icp_grid_blocks(a.n), kIcpBlock, 0, st>>>(a);
+int icp_grid_blocks(int n, int device) {
+    static int cap[64] = {0};
+    if (device >= 0 && device < 64 && !cap[device]) {
+        int sms = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_gn_kernel<kIcpBlock>, kIcpBlock, 0);
+        cap[device] = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int need = (n + kIcpBlock - 1) / kIcpBlock;
+    const int c = (device >= 0 && device < 64) ? cap[device] : 148;
+    const int g = need < c ? need : c;
+    return g > 0 ? g : 1;
+}
+void launch_icp_loop(const IcpArgs& a, const GnLoopCtl& ctl, int grid, cudaStream_t st) {
+    IcpArgs a_ = a;
+    GnLoopCtl c_ = ctl;
+    void* params[] = {&a_, &c_};
+    FLS_CUDA(cudaLaunchCooperativeKernel((const void*)icp_gn_kernel<kIcpBlock>, dim3(grid), dim3(kIcpBlock), params, 0, st));
 }
 
 void launch_fitness(const IvoxView& g, const float4* d_src, int n, const double* T, float max_range, double* d_out2, cudaStream_t st) {

@@ -46,8 +46,8 @@ struct NdtArgs {
     GnState* state;
     double* __restrict__ partials;
 };
-int ndt_grid(int n);
-void launch_ndt_iter(const NdtArgs& a, cudaStream_t st);
+int ndt_grid(int n, int device);  // co-resident grid of the persistent kernel
+void launch_ndt_loop(const NdtArgs& a, const GnLoopCtl& ctl, int grid, cudaStream_t st);
 
 struct IcpArgs {
     const float4* __restrict__ src;  // voxel-filtered scan, body frame
@@ -57,8 +57,8 @@ struct IcpArgs {
     GnState* state;
     double* __restrict__ partials;
 };
-int icp_grid_blocks(int n);
-void launch_icp_iter(const IcpArgs& a, cudaStream_t st);
+int icp_grid_blocks(int n, int device);
+void launch_icp_loop(const IcpArgs& a, const GnLoopCtl& ctl, int grid, cudaStream_t st);
 
 // d_out2[0] = sum of squared NN distances <= max_range, d_out2[1] = how many; T column-major (cast to float inside)
 void launch_fitness(const IvoxView& g, const float4* d_src, int n, const double* T_colmajor, float max_range, double* d_out2, cudaStream_t st);

@@ -261,19 +261,20 @@ __global__ void ndt_update_kernel(NdtUpdateArgs a, int* overflow) {
 }
 
 // ---- K2: NDT residual kernel -----------------------------------------------------------------------------------
+// One persistent launch runs every Gauss-Newton iteration of a Match (gn_handover, fls_gn.cuh): grid-stride over the
+// points, per-thread sums, CTA row, last-CTA fold + solve + release.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) ndt_iter_kernel(NdtArgs a) {
+__global__ void __launch_bounds__(BLOCK) ndt_gn_kernel(NdtArgs a, GnLoopCtl ctl) {
     __shared__ double s_pose[12];
-    if (a.state->done) return;
-    if (threadIdx.x < 9) s_pose[threadIdx.x] = a.state->R[threadIdx.x];
-    else if (threadIdx.x < 12) s_pose[threadIdx.x] = a.state->t[threadIdx.x - 9];
+    for (int it = 0; it < ctl.gp.max_iterations; ++it) {
+    if (threadIdx.x < 9) s_pose[threadIdx.x] = __ldcg(&a.state->R[threadIdx.x]);
+    else if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(&a.state->t[threadIdx.x - 9]);
     __syncthreads();
     double acc[kNumAcc];
 #pragma unroll
     for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.0;
 
-    const int i = blockIdx.x * BLOCK + threadIdx.x;
-    if (i < a.n) {
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < a.n; i += gridDim.x * BLOCK) {
         const float4 sp = a.src[i];
         const double px = sp.x, py = sp.y, pz = sp.z;
         const double* R = s_pose;
@@ -305,8 +306,8 @@ __global__ void __launch_bounds__(BLOCK) ndt_iter_kernel(NdtArgs a) {
             chis += chi;
             ++cnt;
         }
-        acc[kAccHits] = (double)hits;
-        acc[kAccCand] = (double)cnt;
+        acc[kAccHits] += (double)hits;
+        acc[kAccCand] += (double)cnt;
         if (cnt > 0) {
             // B = -R * hat(p)  (3x3), J = [B | I]  (:273-275);  H = [[B^T L B, B^T L],[L B, L]],  err = -[B^T w ; w]
             double B[3][3];
@@ -328,29 +329,44 @@ __global__ void __launch_bounds__(BLOCK) ndt_iter_kernel(NdtArgs a) {
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int c = r; c < 3; ++c) acc[tri6(r, c)] = B[0][r] * LB[0][c] + B[1][r] * LB[1][c] + B[2][r] * LB[2][c];
+                for (int c = r; c < 3; ++c) acc[tri6(r, c)] += B[0][r] * LB[0][c] + B[1][r] * LB[1][c] + B[2][r] * LB[2][c];
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) acc[tri6(r, 3 + c)] = LB[c][r];  // (B^T L)[r][c] = (L B)[c][r], L symmetric
-            acc[tri6(3, 3)] = L0; acc[tri6(3, 4)] = L1; acc[tri6(3, 5)] = L2;
-            acc[tri6(4, 4)] = L3; acc[tri6(4, 5)] = L4; acc[tri6(5, 5)] = L5;
+                for (int c = 0; c < 3; ++c) acc[tri6(r, 3 + c)] += LB[c][r];  // (B^T L)[r][c] = (L B)[c][r], L symmetric
+            acc[tri6(3, 3)] += L0; acc[tri6(3, 4)] += L1; acc[tri6(3, 5)] += L2;
+            acc[tri6(4, 4)] += L3; acc[tri6(4, 5)] += L4; acc[tri6(5, 5)] += L5;
 #pragma unroll
-            for (int r = 0; r < 3; ++r) acc[21 + r] = -(B[0][r] * w0 + B[1][r] * w1 + B[2][r] * w2);
-            acc[24] = -w0; acc[25] = -w1; acc[26] = -w2;
-            acc[kAccValid] = (double)cnt;
-            acc[kAccRes] = chis;
+            for (int r = 0; r < 3; ++r) acc[21 + r] -= (B[0][r] * w0 + B[1][r] * w1 + B[2][r] * w2);
+            acc[24] -= w0; acc[25] -= w1; acc[26] -= w2;
+            acc[kAccValid] += (double)cnt;
+            acc[kAccRes] += chis;
         }
     }
-    block_reduce_store<BLOCK>(acc, a.partials + (size_t)blockIdx.x * kAccStride);
+    if (gn_handover<BLOCK>(acc, ctl, it)) break;
+    }
 }
 
 }  // namespace
 
-int ndt_grid(int n) { return (n + kNdtBlock - 1) / kNdtBlock; }
-void launch_ndt_iter(const NdtArgs& a, cudaStream_t st) {
-    if (a.n <= 0) return;
-    ndt_iter_kernel<kNdtBlock><<<ndt_grid(a.n), kNdtBlock, 0, st>>>(a);
+int ndt_grid(int n, int device) {
+    static int cap[64] = {0};
+    if (device >= 0 && device < 64 && !cap[device]) {
+        int sms = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ndt_gn_kernel<kNdtBlock>, kNdtBlock, 0);
+        cap[device] = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int need = (n + kNdtBlock - 1) / kNdtBlock;
+    const int c = (device >= 0 && device < 64) ? cap[device] : 148;
+    const int g = need < c ? need : c;
+    return g > 0 ? g : 1;
+}
+void launch_ndt_loop(const NdtArgs& a, const GnLoopCtl& ctl, int grid, cudaStream_t st) {
+    NdtArgs a_ = a;
+    GnLoopCtl c_ = ctl;
+    void* params[] = {&a_, &c_};
+    FLS_CUDA(cudaLaunchCooperativeKernel((const void*)ndt_gn_kernel<kNdtBlock>, dim3(grid), dim3(kNdtBlock), params, 0, st));
 }
 
 void NdtMap::configure(double voxel_size, int min_points, int max_points, long long cap) {

@@ -14,9 +14,27 @@ struct MinMax6 {
     float mn[3], mx[3];
 };
 
-__global__ void minmax_kernel(const float4* __restrict__ pts, size_t n, MinMax6* __restrict__ out /*zero-initialised flags handled by host*/,
-                              int* __restrict__ lock) {
-    // block-level min/max, then one atomic section per block (few hundred blocks)
+// order-preserving float <-> uint encoding so the bounding box can be reduced with integer atomicMin / atomicMax
+__device__ __forceinline__ unsigned f2ord(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(unsigned o) {
+    const unsigned u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
+struct MinMaxOrd {
+    unsigned mn[3], mx[3];
+};
+
+__global__ void minmax_kernel(const float4* __restrict__ pts, size_t n, MinMaxOrd* __restrict__ out) {
     __shared__ float s[6][256];
     float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY, mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -35,25 +53,15 @@ __global__ void minmax_kernel(const float4* __restrict__ pts, size_t n, MinMax6*
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        while (atomicCAS(lock, 0, 1) != 0) {}
-        __threadfence();
-        volatile MinMax6* o = out;
-        for (int k = 0; k < 3; ++k) {
-            o->mn[k] = fminf(o->mn[k], s[k][0]);
-            o->mx[k] = fmaxf(o->mx[k], s[3 + k][0]);
-        }
-        __threadfence();
-        atomicExch(lock, 0);
-    }
+    if (threadIdx.x < 3) atomicMin(&out->mn[threadIdx.x], f2ord(s[threadIdx.x][0]));
+    else if (threadIdx.x < 6) atomicMax(&out->mx[threadIdx.x - 3], f2ord(s[threadIdx.x][0]));
 }
 
-__global__ void minmax_init_kernel(MinMax6* o, int* lock) {
+__global__ void minmax_init_kernel(MinMaxOrd* o) {
     for (int k = 0; k < 3; ++k) {
-        o->mn[k] = INFINITY;
-        o->mx[k] = -INFINITY;
+        o->mn[k] = 0xffffffffu;
+        o->mx[k] = 0u;
     }
-    *lock = 0;
 }
 
 __global__ void vg_keys_kernel(const float4* __restrict__ pts, size_t n, float inv, int mb0, int mb1, int mb2, int mul1, int mul2,
@@ -96,15 +104,19 @@ size_t voxel_grid_device(const float4* d_pts, size_t n, float leaf, float4* d_ou
     if (n == 0) return 0;
     const float inv = 1.0f / leaf;
     sc.minmax.reserve(16);
-    MinMax6* d_mm = reinterpret_cast<MinMax6*>(sc.minmax.p);
+    MinMaxOrd* d_mm = reinterpret_cast<MinMaxOrd*>(sc.minmax.p);
     sc.num_runs.reserve(2);
-    int* lock = sc.num_runs.p + 1;
-    minmax_init_kernel<<<1, 1, 0, st>>>(d_mm, lock);
+    minmax_init_kernel<<<1, 1, 0, st>>>(d_mm);
     const unsigned g = grid_for(n, 256) < 592 ? grid_for(n, 256) : 592;
-    minmax_kernel<<<g, 256, 0, st>>>(d_pts, n, d_mm, lock);
-    MinMax6 h;
-    FLS_CUDA(cudaMemcpyAsync(&h, d_mm, sizeof(h), cudaMemcpyDeviceToHost, st));
+    minmax_kernel<<<g, 256, 0, st>>>(d_pts, n, d_mm);
+    MinMaxOrd ho;
+    FLS_CUDA(cudaMemcpyAsync(&ho, d_mm, sizeof(ho), cudaMemcpyDeviceToHost, st));
     FLS_CUDA(cudaStreamSynchronize(st));
+    MinMax6 h;
+    for (int a = 0; a < 3; ++a) {
+        h.mn[a] = ord2f(ho.mn[a]);
+        h.mx[a] = ord2f(ho.mx[a]);
+    }
     if (launches) *launches += 2;
     const long long dx = (long long)((h.mx[0] - h.mn[0]) * inv) + 1, dy = (long long)((h.mx[1] - h.mn[1]) * inv) + 1,
                     dz = (long long)((h.mx[2] - h.mn[2]) * inv) + 1;
