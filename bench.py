@@ -169,18 +169,26 @@ def secondary_kernels(device: int, peak: float, log, steps: int = 6):
                      "kernel_avg_us": 1e3 * k_ms / max(k_n, 1), "roofline_achieved_gbs": ach, "roofline_frac": ach / peak,
                      "cpu_oracle_scans_per_s": 3 / t_cpu, "cpu_threads": orc.num_threads(), "map_points": int(len(mp)), "l2": "warm"}
         log(f"secondary {name}: {out[name]}")
-    proj = synth.make_projected_scan(world, traj[2], kind="livox", seed=13, samples=65000)
-    n = len(proj["ordered"])
     fx = FeatureExtractor(1.0, 0.1, device=device)
-    for _ in range(2):
-        fx.extract_indices(proj["depth"], proj["col"], n, proj["row_start"], proj["row_end"])
-    g_ms = 0.0
-    for _ in range(steps):
-        fx.extract_indices(proj["depth"], proj["col"], n, proj["row_start"], proj["row_end"])
-        g_ms += fx.last_stats.gpu_ms
-    _, _, sec = orc.extract_features(proj["depth"], proj["col"], n, proj["row_start"], proj["row_end"], 1.0, 0.1)
-    out["features_livox_shaped"] = {"points": n, "rows": int(proj["rows"]), "gpu_ms_incl_h2d_d2h": g_ms / steps, "cpu_oracle_ms_1thread": sec * 1e3,
-                                    "algo_gbs": n * 50 / (g_ms / steps * 1e-3) / 1e9}
+    shapes = {"features_livox_shaped": dict(kind="livox", seed=13, samples=65000),
+              "features_hdl64_shaped": dict(kind="spinning", seed=13, sensor="hdl64")}
+    for name, kw in shapes.items():
+        proj = synth.make_projected_scan(world, traj[2], **kw)
+        n = len(proj["ordered"])
+        for _ in range(2):
+            fx.extract_indices(proj["depth"], proj["col"], n, proj["row_start"], proj["row_end"])
+        g_ms = k_ms = 0.0
+        k_b = 0
+        for _ in range(steps):
+            fx.extract_indices(proj["depth"], proj["col"], n, proj["row_start"], proj["row_end"])
+            g_ms += fx.last_stats.gpu_ms
+            k_ms += fx.last_stats.kernel_ms
+            k_b = fx.last_stats.algo_bytes
+        _, _, sec = orc.extract_features(proj["depth"], proj["col"], n, proj["row_start"], proj["row_end"], 1.0, 0.1)
+        ach = k_b / max(k_ms / steps, 1e-9) / 1e6
+        out[name] = {"points": n, "rows": int(proj["rows"]), "gpu_ms_incl_h2d_d2h": g_ms / steps, "kernels_ms": k_ms / steps,
+                     "cpu_oracle_ms_1thread": sec * 1e3, "roofline_achieved_gbs": ach, "roofline_frac": ach / peak}
+        log(f"secondary {name}: {out[name]}")
     return out
 
 

@@ -48,63 +48,112 @@ __device__ __forceinline__ bool grid_nn1(const IvoxView& g, float qx, float qy, 
     return best_j != 0xffffffffu;
 }
 
+// Sub-warp version for the Gauss-Newton loop: kIcpLanes lanes share one query, lane `sub` visits stencil cells
+// sub, sub+kIcpLanes, ...; the winner is the lexicographic minimum of (d2, stencil position, point index) — the same
+// point the sequential scan above keeps (strict '<' in visit order).  All lanes of the group return the result.
+static constexpr int kIcpLanes = 8;
+__device__ __forceinline__ bool grid_nn1_coop(const IvoxView& g, int sub, unsigned group_mask, float qx, float qy, float qz, float& best_d,
+                                              unsigned& best_j, unsigned& n_cand, unsigned& n_hits) {
+    best_d = INFINITY;
+    best_j = 0xffffffffu;
+    unsigned best_s = 0xffffu;
+    n_cand = 0;
+    n_hits = 0;
+    const float ux = __fmul_rn(qx, g.inv_res), uy = __fmul_rn(qy, g.inv_res), uz = __fmul_rn(qz, g.inv_res);
+    const int kx = (int)floorf(ux), ky = (int)floorf(uy), kz = (int)floorf(uz);
+#pragma unroll 1
+    for (int s = sub; s < 27; s += kIcpLanes) {
+        const int cx = kx + c_stencil[s][0], cy = ky + c_stencil[s][1], cz = kz + c_stencil[s][2];
+        unsigned start, count;
+        if (!table_find(g.tab, g.mask, pack_key(cx, cy, cz), start, count)) continue;
+        n_cand += count;
+        n_hits += 1;
+#pragma unroll 2
+        for (unsigned j = start; j < start + count; ++j) {
+            const float4 p = __ldg(g.pts + j);
+            const float d = dist2_ref(p.x, p.y, p.z, qx, qy, qz);
+            if (d < best_d) {
+                best_d = d;
+                best_j = j;
+                best_s = (unsigned)s;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = kIcpLanes / 2; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(group_mask, best_d, o);
+        const unsigned oj = __shfl_xor_sync(group_mask, best_j, o);
+        const unsigned os = __shfl_xor_sync(group_mask, best_s, o);
+        const bool take = (od < best_d) || (od == best_d && (os < best_s || (os == best_s && oj < best_j)));
+        if (take) {
+            best_d = od;
+            best_j = oj;
+            best_s = os;
+        }
+    }
+    return best_j != 0xffffffffu;
+}
+
 // One persistent launch runs every Gauss-Newton iteration of a Match (gn_handover, fls_gn.cuh).
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) icp_gn_kernel(IcpArgs a, GnLoopCtl ctl) {
     __shared__ double s_pose[12];
     __shared__ float s_posef[12];
+    const int sub = threadIdx.x & (kIcpLanes - 1);
+    const unsigned group_mask = ((1u << kIcpLanes) - 1u) << ((threadIdx.x & 31) & ~(kIcpLanes - 1));
+    constexpr int kPerBlock = BLOCK / kIcpLanes;
     for (int it = 0; it < ctl.gp.max_iterations; ++it) {
-    if (threadIdx.x < 12) {
-        const double v = threadIdx.x < 9 ? __ldcg(&a.state->R[threadIdx.x]) : __ldcg(&a.state->t[threadIdx.x - 9]);
-        s_pose[threadIdx.x] = v;
-        s_posef[threadIdx.x] = (float)v;  // R.cast<float>(), t.cast<float>()  (pointcloud_utility.h:145-146)
-    }
-    __syncthreads();
-    double acc[kNumAcc];
-#pragma unroll
-    for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.0;
-
-    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < a.n; i += gridDim.x * BLOCK) {
-        const float4 sp = a.src[i];
-        const float qx = xform_row_f(s_posef[0], s_posef[1], s_posef[2], s_posef[9], sp.x, sp.y, sp.z);
-        const float qy = xform_row_f(s_posef[3], s_posef[4], s_posef[5], s_posef[10], sp.x, sp.y, sp.z);
-        const float qz = xform_row_f(s_posef[6], s_posef[7], s_posef[8], s_posef[11], sp.x, sp.y, sp.z);
-        float d2;
-        unsigned j, nc, nh;
-        const bool found = grid_nn1(a.map, qx, qy, qz, d2, j, nc, nh);
-        acc[kAccCand] += (double)nc;
-        acc[kAccHits] += (double)nh;
-        if (found && !((double)d2 > a.max_corr)) {  // icp_optimized.h:87
-            const float4 m = __ldg(a.map.pts + j);
-            const double e0 = (double)qx - (double)m.x, e1 = (double)qy - (double)m.y, e2 = (double)qz - (double)m.z;
-            const double px = sp.x, py = sp.y, pz = sp.z;
-            const double* R = s_pose;
-            double A[3][3];  // -R * hat(p)   (:100)
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const double r0 = R[r * 3 + 0], r1 = R[r * 3 + 1], r2 = R[r * 3 + 2];
-                A[r][0] = -(r1 * pz - r2 * py);
-                A[r][1] = -(r2 * px - r0 * pz);
-                A[r][2] = -(r0 * py - r1 * px);
-            }
-            // dx = [dt(0..2), dθ(3..5)]:  H = [[I, A],[A^T, A^T A]],  b = -[e ; A^T e]
-            acc[tri6(0, 0)] += 1.0; acc[tri6(1, 1)] += 1.0; acc[tri6(2, 2)] += 1.0;
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) acc[tri6(r, 3 + c)] += A[r][c];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = r; c < 3; ++c) acc[tri6(3 + r, 3 + c)] += A[0][r] * A[0][c] + A[1][r] * A[1][c] + A[2][r] * A[2][c];
-            acc[21] -= e0; acc[22] -= e1; acc[23] -= e2;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) acc[24 + r] -= (A[0][r] * e0 + A[1][r] * e1 + A[2][r] * e2);
-            acc[kAccValid] += 1.0;
-            acc[kAccRes] += sqrt(e0 * e0 + e1 * e1 + e2 * e2);  // total_res += error.norm()  (:126)
+        if (threadIdx.x < 12) {
+            const double v = threadIdx.x < 9 ? __ldcg(&a.state->R[threadIdx.x]) : __ldcg(&a.state->t[threadIdx.x - 9]);
+            s_pose[threadIdx.x] = v;
+            s_posef[threadIdx.x] = (float)v;  // R.cast<float>(), t.cast<float>()  (pointcloud_utility.h:145-146)
         }
-    }
-    if (gn_handover<BLOCK>(acc, ctl, it)) break;
+        __syncthreads();
+        double acc[kNumAcc];
+#pragma unroll
+        for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.0;
+
+        for (int i = blockIdx.x * kPerBlock + threadIdx.x / kIcpLanes; i < a.n; i += gridDim.x * kPerBlock) {
+            const float4 sp = a.src[i];
+            const float qx = xform_row_f(s_posef[0], s_posef[1], s_posef[2], s_posef[9], sp.x, sp.y, sp.z);
+            const float qy = xform_row_f(s_posef[3], s_posef[4], s_posef[5], s_posef[10], sp.x, sp.y, sp.z);
+            const float qz = xform_row_f(s_posef[6], s_posef[7], s_posef[8], s_posef[11], sp.x, sp.y, sp.z);
+            float d2;
+            unsigned j, nc, nh;
+            const bool found = grid_nn1_coop(a.map, sub, group_mask, qx, qy, qz, d2, j, nc, nh);
+            acc[kAccCand] += (double)nc;
+            acc[kAccHits] += (double)nh;
+            if (sub == 0 && found && !((double)d2 > a.max_corr)) {  // icp_optimized.h:87
+                const float4 m = __ldg(a.map.pts + j);
+                const double e0 = (double)qx - (double)m.x, e1 = (double)qy - (double)m.y, e2 = (double)qz - (double)m.z;
+                const double px = sp.x, py = sp.y, pz = sp.z;
+                const double* R = s_pose;
+                double A[3][3];  // -R * hat(p)   (:100)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double r0 = R[r * 3 + 0], r1 = R[r * 3 + 1], r2 = R[r * 3 + 2];
+                    A[r][0] = -(r1 * pz - r2 * py);
+                    A[r][1] = -(r2 * px - r0 * pz);
+                    A[r][2] = -(r0 * py - r1 * px);
+                }
+                // dx = [dt(0..2), dθ(3..5)]:  H = [[I, A],[A^T, A^T A]],  b = -[e ; A^T e]
+                acc[tri6(0, 0)] += 1.0; acc[tri6(1, 1)] += 1.0; acc[tri6(2, 2)] += 1.0;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) acc[tri6(r, 3 + c)] += A[r][c];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = r; c < 3; ++c) acc[tri6(3 + r, 3 + c)] += A[0][r] * A[0][c] + A[1][r] * A[1][c] + A[2][r] * A[2][c];
+                acc[21] -= e0; acc[22] -= e1; acc[23] -= e2;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) acc[24 + r] -= (A[0][r] * e0 + A[1][r] * e1 + A[2][r] * e2);
+                acc[kAccValid] += 1.0;
+                acc[kAccRes] += sqrt(e0 * e0 + e1 * e1 + e2 * e2);  // total_res += error.norm()  (:126)
+            }
+        }
+        if (gn_handover<BLOCK>(acc, ctl, it)) break;
     }
 }
 
@@ -156,7 +205,8 @@ int icp_grid_blocks(int n, int device) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_gn_kernel<kIcpBlock>, kIcpBlock, 0);
         cap[device] = sms * (per_sm > 0 ? per_sm : 1);
     }
-    const int need = (n + kIcpBlock - 1) / kIcpBlock;
+    const int per_block = kIcpBlock / kIcpLanes;
+    const int need = (n + per_block - 1) / per_block;
     const int c = (device >= 0 && device < 64) ? cap[device] : 148;
     const int g = need < c ? need : c;
     return g > 0 ? g : 1;

@@ -66,3 +66,40 @@ def test_degenerate_rows():
     gc, gp = fx.extract_indices(depth, col, n, rs, re)
     oc, op, _ = orc.extract_features(depth, col, n, rs, re, 1.0, 0.1)
     assert np.array_equal(gc, oc) and np.array_equal(gp, op)
+
+
+def _ring_case(depth_rows, col_step=1):
+    counts = [len(d) for d in depth_rows]
+    depth = np.concatenate(depth_rows).astype(np.float32)
+    col = np.concatenate([np.arange(c) * col_step for c in counts]).astype(np.int32)
+    ends = np.cumsum(counts)
+    rs = (ends - np.array(counts) + 5).astype(np.int32)
+    re = (ends - 6).astype(np.int32)
+    return {"ordered": np.zeros((len(depth), 4), np.float32), "depth": depth, "col": col, "row_start": rs, "row_end": re}
+
+
+def _noisy_rows(seed, sizes, sigma):
+    rng = np.random.default_rng(seed)
+    return [12.0 + 3.0 * np.sin(np.arange(c) / 90.0) + rng.normal(0, sigma, c) for c in sizes]
+
+
+def test_sequential_tail_of_greedy_passes(monkeypatch):
+    """The round-parallel greedy passes hand the undecided rest to one thread after `max_rounds` rounds (monotone
+    roughness ramps decide one point per round); forcing that hand-over after 1 and 3 rounds must not change a bit."""
+    rows = _noisy_rows(21, (300, 2500, 7000), 0.01)
+    ref = _check(_ring_case(rows), 0.02, 0.004)
+    assert len(ref[0]) > 40
+    for rounds in ("1", "3"):
+        monkeypatch.setenv("FLS_FEAT_MAX_ROUNDS", rounds)
+        got = _check(_ring_case(rows), 0.02, 0.004)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+
+
+def test_corner_limit_and_dense_corners():
+    """Range noise large enough that most points qualify as corners: each block hits the 20-pick limit and the 21st
+    candidate must be left untouched for the planar pass."""
+    rows = _noisy_rows(8, (400, 1900, 5000), 0.03)
+    gc, _ = _check(_ring_case(rows), 0.05, 0.001)
+    assert len(gc) > 250  # the two long rings saturate at 6 x 20
+    _check(_ring_case(rows, col_step=3), 0.05, 0.001)     # column gaps of 3: reach stays 5 (|dcol| <= 10 per step)
+    _check(_ring_case(rows, col_step=11), 0.05, 0.001)    # gaps > 10: no suppression reach at all
