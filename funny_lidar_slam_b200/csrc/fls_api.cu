@@ -37,6 +37,18 @@ Handle::Handle(const fls_config& c) : cfg(c) {
     icp_grid.key_mode = 1;
     icp_grid.set_resolution((float)(std::sqrt(cfg.icp_max_correspond_distance > 0 ? cfg.icp_max_correspond_distance : 1.0) * 1.001));
     fit_grid.key_mode = 1;
+    // exact-search grids of the kd-tree plug-ins: LoamFull only needs neighbours inside sqrt(point_search_thres), so a cell
+    // of that size settles every query in the 27-cell pass; the ungated point-to-plane variant uses ~2 map leafs
+    kd_planar.grid.key_mode = kd_corner.grid.key_mode = 1;
+    if (cfg.method == FLS_LOAM_FULL) {
+        const float c = (float)(std::sqrt(cfg.point_search_thres > 0 ? cfg.point_search_thres : 1.0) * 1.001);
+        kd_planar.grid.set_resolution(c);
+        kd_corner.grid.set_resolution(c);
+    } else {
+        const float c = 2.0f * (cfg.map_cloud_filter_size > 0.f ? cfg.map_cloud_filter_size : 0.5f);
+        kd_planar.grid.set_resolution(c < 0.8f ? 0.8f : c);
+        kd_corner.grid.set_resolution(1.0f);
+    }
     profile = (cfg.flags & FLS_FLAG_PROFILE) != 0;
     if (profile) {
         prof_ev.resize(2 * (size_t)(cfg.max_iterations > 0 ? cfg.max_iterations : 1));
@@ -313,6 +325,34 @@ static void mat3_from_T(const double* T, double* R) {
         for (int c = 0; c < 3; ++c) R[r * 3 + c] = T[c * 4 + r];
 }
 
+// IsNeedAddCloud (icp_optimized.h:218-236, loam_point_to_plane_kdtree.h:186-202, loam_full_kdtree.h:356-371): key-frame
+// gating on translation / RPY deltas against a persistent last_T that starts at the first pose it sees  [quirk 7]
+bool Handle::need_add_cloud(const double* T, double* last_T, bool* have_last) const {
+    if (!*have_last) {
+        std::memcpy(last_T, T, 16 * sizeof(double));
+        *have_last = true;
+    }
+    double Rl[9], Rc[9], Rli[9], Rd[9];
+    mat3_from_T(last_T, Rl);
+    mat3_from_T(T, Rc);
+    {  // 3x3 inverse by cofactors
+        const double c00 = Rl[4] * Rl[8] - Rl[5] * Rl[7], c01 = Rl[5] * Rl[6] - Rl[3] * Rl[8], c02 = Rl[3] * Rl[7] - Rl[4] * Rl[6];
+        const double id = 1.0 / (Rl[0] * c00 + Rl[1] * c01 + Rl[2] * c02);
+        Rli[0] = c00 * id; Rli[1] = (Rl[2] * Rl[7] - Rl[1] * Rl[8]) * id; Rli[2] = (Rl[1] * Rl[5] - Rl[2] * Rl[4]) * id;
+        Rli[3] = c01 * id; Rli[4] = (Rl[0] * Rl[8] - Rl[2] * Rl[6]) * id; Rli[5] = (Rl[2] * Rl[3] - Rl[0] * Rl[5]) * id;
+        Rli[6] = c02 * id; Rli[7] = (Rl[1] * Rl[6] - Rl[0] * Rl[7]) * id; Rli[8] = (Rl[0] * Rl[4] - Rl[1] * Rl[3]) * id;
+    }
+    mat3_mul(Rli, Rc, Rd);
+    const double roll = std::atan2(Rd[7], Rd[8]), pitch = std::asin(-Rd[6]), yaw = std::atan2(Rd[3], Rd[0]);
+    const double dt[3] = {T[12] - last_T[12], T[13] - last_T[13], T[14] - last_T[14]};
+    if (norm3(dt) > cfg.dist_thre_add_cloud || std::fabs(roll) > cfg.rot_thre_add_cloud || std::fabs(pitch) > cfg.rot_thre_add_cloud ||
+        std::fabs(yaw) > cfg.rot_thre_add_cloud) {
+        std::memcpy(last_T, T, 16 * sizeof(double));
+        return true;
+    }
+    return false;
+}
+
 int Handle::match_icp(const float4* d_in, size_t n_in, double* T, int* converged, fls_match_stats* st) {
     if (n_in <= 10) return FLS_ERR_TOO_FEW_POINTS;  // CHECK_GT(ordered_cloud_.size(), 10u)  (:55)
     if (icp_grid.n_pts == 0) return FLS_ERR_NO_MAP;
@@ -345,26 +385,7 @@ int Handle::match_icp(const float4* d_in, size_t n_in, double* T, int* converged
     if (rc != FLS_OK) return rc;
     if (h_state->converged && !cfg.localization_mode) {
         // IsNeedAddCloud (:218-236): key-frame gating on translation / RPY deltas against a persistent last_T
-        if (!icp_have_last) {
-            std::memcpy(icp_last_T, T, sizeof(icp_last_T));
-            icp_have_last = true;
-        }
-        double Rl[9], Rc[9], Rli[9], Rd[9];
-        mat3_from_T(icp_last_T, Rl);
-        mat3_from_T(T, Rc);
-        {  // 3x3 inverse by cofactors
-            const double c00 = Rl[4] * Rl[8] - Rl[5] * Rl[7], c01 = Rl[5] * Rl[6] - Rl[3] * Rl[8], c02 = Rl[3] * Rl[7] - Rl[4] * Rl[6];
-            const double id = 1.0 / (Rl[0] * c00 + Rl[1] * c01 + Rl[2] * c02);
-            Rli[0] = c00 * id; Rli[1] = (Rl[2] * Rl[7] - Rl[1] * Rl[8]) * id; Rli[2] = (Rl[1] * Rl[5] - Rl[2] * Rl[4]) * id;
-            Rli[3] = c01 * id; Rli[4] = (Rl[0] * Rl[8] - Rl[2] * Rl[6]) * id; Rli[5] = (Rl[2] * Rl[3] - Rl[0] * Rl[5]) * id;
-            Rli[6] = c02 * id; Rli[7] = (Rl[1] * Rl[6] - Rl[0] * Rl[7]) * id; Rli[8] = (Rl[0] * Rl[4] - Rl[1] * Rl[3]) * id;
-        }
-        mat3_mul(Rli, Rc, Rd);
-        const double roll = std::atan2(Rd[7], Rd[8]), pitch = std::asin(-Rd[6]), yaw = std::atan2(Rd[3], Rd[0]);
-        const double dt[3] = {T[12] - icp_last_T[12], T[13] - icp_last_T[13], T[14] - icp_last_T[14]};
-        if (norm3(dt) > cfg.dist_thre_add_cloud || std::fabs(roll) > cfg.rot_thre_add_cloud || std::fabs(pitch) > cfg.rot_thre_add_cloud ||
-            std::fabs(yaw) > cfg.rot_thre_add_cloud) {
-            std::memcpy(icp_last_T, T, sizeof(icp_last_T));
+        if (need_add_cloud(T, icp_last_T, &icp_have_last)) {
             stage.reserve(n);
             launch_transform_f(src_f.p, n, T, stage.p, stream);  // :156 TransformPointCloud(source, final) in float
             launches++;
@@ -377,10 +398,141 @@ int Handle::match_icp(const float4* d_in, size_t n_in, double* T, int* converged
     return FLS_OK;
 }
 
+// ---- LoamPointToPlaneKdtree / LoamFull -------------------------------------------------------------------------------
+static LoamGrid loam_grid_of(const Handle::WindowMap& w) {
+    LoamGrid g;
+    g.pts = w.grid.pts_sorted.p;
+    g.tab = w.grid.table.p;
+    g.mask = w.grid.mask;
+    g.inv_cell = w.grid.inv_res;
+    g.cell = w.grid.res;
+    g.n_pts = (unsigned)w.grid.n_pts;
+    return g;
+}
+
+int Handle::window_add(WindowMap& w, const float4* d_cloud, size_t n, size_t window, float leaf, int filter_mode, bool replace) {
+    const float4* merged = d_cloud;
+    size_t n_merged = n;
+    size_t depth = 1;
+    if (!replace) {
+        std::unique_ptr<Cloud> c(new Cloud());
+        c->buf.reserve(n);
+        if (n) FLS_CUDA(cudaMemcpyAsync(c->buf.p, d_cloud, n * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        c->n = n;
+        w.deque.push_back(std::move(c));
+        if (w.deque.size() > window) {
+            FLS_CUDA(cudaStreamSynchronize(stream));  // the evicted buffer may still feed a copy in flight
+            w.deque.pop_front();
+        }
+        n_merged = 0;
+        for (auto& q : w.deque) n_merged += q->n;
+        w.merged.reserve(n_merged);
+        size_t off = 0;
+        for (auto& q : w.deque) {
+            if (q->n) FLS_CUDA(cudaMemcpyAsync(w.merged.p + off, q->buf.p, q->n * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+            off += q->n;
+        }
+        merged = w.merged.p;
+        depth = w.deque.size();
+    }
+    w.cloud.reserve(n_merged);
+    if (filter_mode == 0 || depth > 5) {
+        w.n = voxel_grid_device(merged, n_merged, leaf, w.cloud.p, scratch, stream, &launches);
+    } else {
+        if (n_merged) FLS_CUDA(cudaMemcpyAsync(w.cloud.p, merged, n_merged * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        w.n = n_merged;
+    }
+    w.grid.clear();
+    const int rc = w.grid.append_and_build(w.cloud.p, w.n, 0, stream);
+    launches += w.grid.launches;
+    w.grid.launches = 0;
+    return rc;
+}
+
+int Handle::add_cloud_kd(const float4* d_planar, size_t n_planar, const float4* d_corner, size_t n_corner) {
+    if (cfg.method == FLS_P2PLANE_KNN) {
+        // loam_point_to_plane_kdtree.h:56-80: localization mode replaces the map, mapping mode slides a window; both
+        // end in VoxelGridCloud(local_map, map_cloud_filter_size) + kd-tree
+        const int rc = window_add(kd_planar, d_planar, n_planar, (size_t)cfg.local_map_size, cfg.map_cloud_filter_size, 0,
+                                  cfg.localization_mode != 0);
+        if (rc == FLS_OK) set_fit_cloud(kd_planar.cloud.p, kd_planar.n);  // GetFitnessScore searches the same tree (:159-183)
+        return rc;
+    }
+    // loam_full_kdtree.h:66-104: {planar, corner}, both windows slide, filters only beyond 5 clouds
+    int rc = window_add(kd_planar, d_planar, n_planar, (size_t)cfg.local_map_size, cfg.map_cloud_filter_size, 1, false);
+    if (rc != FLS_OK) return rc;
+    return window_add(kd_corner, d_corner, n_corner, (size_t)cfg.corner_local_map_size, cfg.corner_map_filter_size, 1, false);
+}
+
+int Handle::match_kd(const float4* d_planar, size_t n_planar, const float4* d_corner, size_t n_corner, double* T, int* converged,
+                     fls_match_stats* st) {
+    const bool full = cfg.method == FLS_LOAM_FULL;
+    if (kd_planar.n == 0) return FLS_ERR_NO_MAP;
+    if (!full) n_corner = 0;
+    const size_t n = n_planar + n_corner;
+    const int ni = (int)n;
+    const int grid = loam_grid_blocks(ni, cfg.device);
+    GnLoopCtl ctl = make_ctl(*this, cfg.method, grid, 50);
+    launch_gn_init(state.p, T, stream, sync_buf.p, 2 * cfg.max_iterations + 2);
+    launches++;
+    rec_d.reserve(n * 8 + 8);
+    flags.reserve(n + 1);
+    LoamArgs a;
+    a.corner = d_corner;
+    a.n_corner = (int)n_corner;
+    a.planar = d_planar;
+    a.n_planar = (int)n_planar;
+    a.planar_map = loam_grid_of(kd_planar);
+    a.corner_map = full ? loam_grid_of(kd_corner) : a.planar_map;
+    a.plane_thres = cfg.point_to_planar_thres;
+    a.search_thres = full ? cfg.point_search_thres : INFINITY;
+    a.line_ratio = cfg.line_ratio_thres;
+    a.gate = full ? (float)cfg.point_search_thres * 1.0001f : INFINITY;
+    a.state = state.p;
+    a.rec = rec_d.p;
+    a.flags = flags.p;
+    // roofline accounting (K5): 16 B source point + 27 x 16 B slot probes + 56 B persistent record, 16 B per scanned map record
+    per_point_iter_bytes = 16 + 16LL * 27 + 56;
+    per_cand_bytes = 16;
+    per_hit_bytes = 0;
+    if (profile) FLS_CUDA(cudaEventRecord(prof_ev[0], stream));
+    launch_loam_loop(a, ctl, grid, stream);
+    if (profile) FLS_CUDA(cudaEventRecord(prof_ev[1], stream));
+    launches += 2;
+    fused_loop = true;
+    last_src = d_planar;
+    last_src_n = n_planar;
+    const int rc = finish_match(T, converged, st, (long long)n);
+    if (rc != FLS_OK) return rc;
+    // key-frame insertion: loam_point_to_plane_kdtree.h:146-150 (gate evaluated before the mode test), loam_full_kdtree.h:178-186
+    if (h_state->converged && need_add_cloud(T, kd_last_T, &kd_have_last) && (full || !cfg.localization_mode)) {
+        int rc2;
+        if (full) {
+            stage.reserve(n_planar);
+            stage2.reserve(n_corner);
+            launch_transform_d(d_planar, n_planar, T, stage.p, stream);  // pcl::transformPointCloud(cloud, out, T_) with the double matrix
+            launch_transform_d(d_corner, n_corner, T, stage2.p, stream);
+            launches += 2;
+            rc2 = add_cloud_kd(stage.p, n_planar, stage2.p, n_corner);
+        } else {
+            stage.reserve(n_planar);
+            launch_transform_f(d_planar, n_planar, T, stage.p, stream);  // TransformPointCloud(source, final): fp32 with R, t cast to float
+            launches++;
+            rc2 = add_cloud_kd(stage.p, n_planar, nullptr, 0);
+        }
+        FLS_CUDA(cudaStreamSynchronize(stream));
+        if (st) st->gpu_launches = launches;
+        if (rc2 != FLS_OK) return rc2;
+    }
+    return FLS_OK;
+}
+
 // ---- GetFitnessScore -------------------------------------------------------------------------------------------------
 int Handle::fitness(float max_range, float* score) {
     *score = 3.402823466e+38f;  // FloatNaN / "no inliers" upstream
-    if (cfg.method != FLS_ICP_P2P && !cfg.localization_mode) return FLS_OK;  // FloatNaN outside localization mode
+    if (cfg.method == FLS_LOAM_FULL) return FLS_OK;  // loam_full_kdtree.h:206-208 FloatNaN
+    // ICP and the kd-tree point-to-plane plug-in always search their tree; NDT / iVox return FloatNaN outside localization mode
+    if (cfg.method != FLS_ICP_P2P && cfg.method != FLS_P2PLANE_KNN && !cfg.localization_mode) return FLS_OK;
     if (fit_cloud_n == 0 || last_src == nullptr || last_src_n == 0 || !(max_range > 0.f)) return FLS_OK;
     begin_call();
     if (fit_grid_version != fit_cloud_version || fit_grid_range != max_range) {
@@ -598,8 +750,15 @@ static int validate(const fls_config* c) {
         if (!(c->icp_max_correspond_distance > 0) || !(c->icp_max_correspond_distance < 1e300) || !(c->source_cloud_filter_size > 0.f) ||
             !(c->map_cloud_filter_size > 0.f) || c->local_map_size <= 0)
             return FLS_ERR_INVALID_ARG;
+    } else if (c->method == FLS_P2PLANE_KNN) {
+        if (!(c->point_to_planar_thres < 1e300) || !(c->rot_thre_add_cloud < 1e300) || !(c->dist_thre_add_cloud < 1e300) ||
+            !(c->map_cloud_filter_size > 0.f) || c->local_map_size <= 0)
+            return FLS_ERR_INVALID_ARG;  // loam_point_to_plane_kdtree.h:43-50
     } else {
-        return FLS_ERR_UNSUPPORTED;  // PointToPlane_KdTree / LoamFull_KdTree: SURVEY.md §8f row 3, not built yet
+        if (!(c->point_to_planar_thres < 1e300) || !(c->point_search_thres < 1e300) || !(c->point_search_thres > 0) ||
+            !(c->line_ratio_thres < 1e300) || !(c->rot_thre_add_cloud < 1e300) || !(c->dist_thre_add_cloud < 1e300) ||
+            !(c->map_cloud_filter_size > 0.f) || !(c->corner_map_filter_size > 0.f) || c->local_map_size <= 0 || c->corner_local_map_size <= 0)
+            return FLS_ERR_INVALID_ARG;  // loam_full_kdtree.h:41-53
     }
     return FLS_OK;
 }
@@ -626,8 +785,11 @@ void fls_destroy(fls_handle* h) { delete reinterpret_cast<Handle*>(h); }
 int fls_add_cloud(fls_handle* hh, int n_clouds, const void* const* pts, const size_t* n, size_t stride) {
     Handle* h = reinterpret_cast<Handle*>(hh);
     if (!h || !pts || !n || n_clouds < 1 || !stride_ok(stride)) return FLS_ERR_INVALID_ARG;
-    if (n_clouds != 1) return FLS_ERR_INVALID_ARG;  // CHECK_EQ(cloud_list.size(), 1) in all three built plug-ins
-    if (!pts[0] && n[0]) return FLS_ERR_INVALID_ARG;
+    // CHECK_EQ(cloud_list.size(), 1) everywhere except LoamFull, which takes {planar, corner} (loam_full_kdtree.h:66-68)
+    const int want = h->cfg.method == FLS_LOAM_FULL ? 2 : 1;
+    if (n_clouds != want) return FLS_ERR_INVALID_ARG;
+    for (int k = 0; k < n_clouds; ++k)
+        if (!pts[k] && n[k]) return FLS_ERR_INVALID_ARG;
     FLS_TRY
     h->begin_call();
     int rc = FLS_ERR_UNSUPPORTED;
@@ -635,6 +797,13 @@ int fls_add_cloud(fls_handle* hh, int n_clouds, const void* const* pts, const si
         case FLS_P2PLANE_IVOX: rc = h->add_cloud_ivox(pts[0], n[0], stride); break;
         case FLS_NDT: rc = h->add_cloud_ndt(h->upload(pts[0], n[0], stride, h->stage), n[0]); break;
         case FLS_ICP_P2P: rc = h->add_cloud_icp(h->upload(pts[0], n[0], stride, h->stage), n[0]); break;
+        case FLS_P2PLANE_KNN: rc = h->add_cloud_kd(h->upload(pts[0], n[0], stride, h->stage), n[0], nullptr, 0); break;
+        case FLS_LOAM_FULL: {
+            const float4* dp = h->upload(pts[0], n[0], stride, h->stage);
+            const float4* dc = h->upload(pts[1], n[1], stride, h->stage2);
+            rc = h->add_cloud_kd(dp, n[0], dc, n[1]);
+            break;
+        }
         default: break;
     }
     h->end_call(nullptr);
@@ -642,12 +811,14 @@ int fls_add_cloud(fls_handle* hh, int n_clouds, const void* const* pts, const si
     FLS_CATCH
 }
 
-static int match_dispatch(Handle* h, const float4* d_ordered, size_t n_ordered, const float4* d_planar, size_t n_planar, double* T,
-                          int* converged, fls_match_stats* st) {
+static int match_dispatch(Handle* h, const float4* d_ordered, size_t n_ordered, const float4* d_planar, size_t n_planar, const float4* d_corner,
+                          size_t n_corner, double* T, int* converged, fls_match_stats* st) {
     switch (h->cfg.method) {
         case FLS_P2PLANE_IVOX: return h->match_p2plane_ivox(d_planar, n_planar, T, converged, st);
         case FLS_NDT: return h->match_ndt(d_ordered, n_ordered, T, converged, st);
         case FLS_ICP_P2P: return h->match_icp(d_ordered, n_ordered, T, converged, st);
+        case FLS_P2PLANE_KNN:
+        case FLS_LOAM_FULL: return h->match_kd(d_planar, n_planar, d_corner, n_corner, T, converged, st);
         default: return FLS_ERR_UNSUPPORTED;
     }
 }
@@ -656,22 +827,27 @@ int fls_match(fls_handle* hh, const void* ordered, size_t n_ordered, const void*
               size_t stride, double T[16], int* converged, fls_match_stats* st) {
     Handle* h = reinterpret_cast<Handle*>(hh);
     if (!h || !T || !stride_ok(stride)) return FLS_ERR_INVALID_ARG;
-    (void)corner;
-    (void)n_corner;
     FLS_TRY
     if (st) std::memset(st, 0, sizeof(*st));
     h->begin_call();
     const float4* d_ord = nullptr;
     const float4* d_pla = nullptr;
+    const float4* d_cor = nullptr;
     const bool uses_planar = h->cfg.method >= FLS_P2PLANE_IVOX;
     if (uses_planar) {
         if (!planar && n_planar) return FLS_ERR_INVALID_ARG;
         d_pla = h->upload(planar, n_planar, stride, h->src);
+        if (h->cfg.method == FLS_LOAM_FULL) {
+            if (!corner && n_corner) return FLS_ERR_INVALID_ARG;
+            d_cor = h->upload(corner, n_corner, stride, h->src2);
+        } else {
+            n_corner = 0;
+        }
     } else {
         if (!ordered && n_ordered) return FLS_ERR_INVALID_ARG;
         d_ord = h->upload(ordered, n_ordered, stride, h->src);
     }
-    return match_dispatch(h, d_ord, n_ordered, d_pla, n_planar, T, converged, st);
+    return match_dispatch(h, d_ord, n_ordered, d_pla, n_planar, d_cor, n_corner, T, converged, st);
     FLS_CATCH
 }
 
@@ -682,7 +858,8 @@ int fls_match_device(fls_handle* hh, const void* d_points, size_t n, double T[16
     if (st) std::memset(st, 0, sizeof(*st));
     h->begin_call();
     const float4* d = static_cast<const float4*>(d_points);
-    return match_dispatch(h, d, n, d, n, T, converged, st);
+    if (h->cfg.method == FLS_LOAM_FULL) return FLS_ERR_UNSUPPORTED;  // two feature clouds: use fls_match
+    return match_dispatch(h, d, n, d, n, nullptr, 0, T, converged, st);
     FLS_CATCH
 }
 
@@ -720,6 +897,12 @@ int fls_get_map_info(const fls_handle* hh, fls_map_info* out) {
         out->n_voxels = (long long)h->icp_grid.n_vox;
         out->table_slots = h->icp_grid.n_pts ? (long long)h->icp_grid.mask + 1 : 0;
         out->bytes = (long long)h->icp_grid.bytes();
+    } else {  // kd-tree plug-ins: planar map (+ corner map for LoamFull)
+        const bool full = h->cfg.method == FLS_LOAM_FULL;
+        out->n_points = (long long)(h->kd_planar.n + (full ? h->kd_corner.n : 0));
+        out->n_voxels = (long long)(h->kd_planar.grid.n_vox + (full ? h->kd_corner.grid.n_vox : 0));
+        out->table_slots = (h->kd_planar.n ? (long long)h->kd_planar.grid.mask + 1 : 0) + (full && h->kd_corner.n ? (long long)h->kd_corner.grid.mask + 1 : 0);
+        out->bytes = (long long)(h->kd_planar.grid.bytes() + h->kd_planar.cloud.bytes() + (full ? h->kd_corner.grid.bytes() + h->kd_corner.cloud.bytes() : 0));
     }
     return FLS_OK;
 }

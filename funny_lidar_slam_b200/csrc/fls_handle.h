@@ -63,6 +63,20 @@ struct Handle {
     bool icp_have_last = false;                    // `static last_T` of IsNeedAddCloud (:219)  [quirk 7]
     double icp_last_T[16];
 
+    // kd-tree LOAM plug-ins (LoamPointToPlaneKdtree, LoamFull): sliding window of clouds -> VoxelGrid -> exact search grid
+    struct WindowMap {
+        std::deque<std::unique_ptr<Cloud>> deque;  // cloud_deque_ / planar_cloud_deque_ / corner_cloud_deque_
+        DevBuf<float4> merged;                     // concatenation of the window
+        DevBuf<float4> cloud;                      // what upstream builds the kd-tree on
+        size_t n = 0;
+        IvoxMap grid;                              // floor-keyed uniform grid over `cloud`
+    };
+    WindowMap kd_planar, kd_corner;
+    bool kd_have_last = false;  // `static last_T` of IsNeedAddCloud  [quirk 7]
+    double kd_last_T[16];
+    DevBuf<double> rec_d;       // persistent {J[6], residual} records of the kd-tree plug-ins
+    DevBuf<float4> src2;        // uploaded corner features (LoamFull)
+
     // GetFitnessScore support: cloud the upstream kd-tree is built on + a search grid sized for max_range
     DevBuf<float4> fit_cloud;
     size_t fit_cloud_n = 0;
@@ -92,6 +106,12 @@ struct Handle {
 
     int add_cloud_icp(const float4* d_cloud, size_t n);
     int match_icp(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st);
+
+    // filter_mode 0: always VoxelGrid(leaf); 1: only once the window holds more than 5 clouds (loam_full_kdtree.h:91-99)
+    int window_add(WindowMap& w, const float4* d_cloud, size_t n, size_t window, float leaf, int filter_mode, bool replace);
+    int add_cloud_kd(const float4* d_planar, size_t n_planar, const float4* d_corner, size_t n_corner);
+    int match_kd(const float4* d_planar, size_t n_planar, const float4* d_corner, size_t n_corner, double* T, int* converged, fls_match_stats* st);
+    bool need_add_cloud(const double* T, double* last_T, bool* have_last) const;
 
     int fitness(float max_range, float* score);
 };

@@ -10,6 +10,7 @@ namespace fls {
 static constexpr int kP2PlaneBlock = 384;  // 12 warps: consecutive chunks share L1, and the hand-over folds 3x fewer CTA rows
 static constexpr int kNdtBlock = 128;
 static constexpr int kIcpBlock = 128;
+static constexpr int kLoamBlock = 128;
 
 // whole-loop arguments of the persistent LoamPointToPlaneIVOX kernel (K1 + fused K6)
 struct P2PlaneLoopArgs {
@@ -59,6 +60,31 @@ struct IcpArgs {
 };
 int icp_grid_blocks(int n, int device);
 void launch_icp_loop(const IcpArgs& a, const GnLoopCtl& ctl, int grid, cudaStream_t st);
+
+// K5 — kd-tree LOAM plug-ins (LoamPointToPlaneKdtree, LoamFull): exact unbounded 5-NN over a uniform grid
+struct LoamGrid {
+    const float4* __restrict__ pts;    // cell-contiguous map points
+    const HashSlot* __restrict__ tab;  // floor-keyed occupied-cell table
+    unsigned mask;
+    float inv_cell, cell;
+    unsigned n_pts;
+};
+struct LoamArgs {
+    const float4* __restrict__ corner;  // body-frame corner features (LoamFull only)
+    int n_corner;
+    const float4* __restrict__ planar;  // body-frame planar features
+    int n_planar;
+    LoamGrid corner_map, planar_map;
+    double plane_thres;    // point_to_planar_thres
+    double search_thres;   // point_search_thres on the 5th squared distance (+inf: none)
+    double line_ratio;     // line_ratio_thres
+    float gate;            // search_thres as the search's stop bound
+    GnState* state;
+    double* __restrict__ rec;  // [n_corner + n_planar][8] persistent {J[6], residual, -}
+    unsigned char* __restrict__ flags;
+};
+int loam_grid_blocks(int n, int device);
+void launch_loam_loop(const LoamArgs& a, const GnLoopCtl& ctl, int grid, cudaStream_t st);
 
 // d_out2[0] = sum of squared NN distances <= max_range, d_out2[1] = how many; T column-major (cast to float inside)
 void launch_fitness(const IvoxView& g, const float4* d_src, int n, const double* T_colmajor, float max_range, double* d_out2, cudaStream_t st);

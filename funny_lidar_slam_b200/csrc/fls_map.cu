@@ -135,7 +135,23 @@ __global__ void transform_f_kernel(const float4* __restrict__ in, size_t n, floa
                          xform_row_f(r6, r7, r8, t2, p.x, p.y, p.z), p.w);
 }
 
+// pcl::transformPoint / pcl::transformPointCloud with a double transform: fp64 R·p + t, stored back as fp32
+__global__ void transform_d_kernel(const float4* __restrict__ in, size_t n, double r0, double r1, double r2, double r3, double r4, double r5,
+                                   double r6, double r7, double r8, double t0, double t1, double t2, float4* __restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = in[i];
+    out[i] = make_float4(xform_row_d(r0, r1, r2, t0, (double)p.x, (double)p.y, (double)p.z),
+                         xform_row_d(r3, r4, r5, t1, (double)p.x, (double)p.y, (double)p.z),
+                         xform_row_d(r6, r7, r8, t2, (double)p.x, (double)p.y, (double)p.z), p.w);
+}
+
 }  // namespace
+
+void launch_transform_d(const float4* d_in, size_t n, const double* T, float4* d_out, cudaStream_t st) {
+    if (n == 0) return;
+    transform_d_kernel<<<grid_for(n, 256), 256, 0, st>>>(d_in, n, T[0], T[4], T[8], T[1], T[5], T[9], T[2], T[6], T[10], T[12], T[13], T[14], d_out);
+}
 
 void launch_repack(const unsigned char* d_raw, size_t n, size_t stride, float4* d_out, cudaStream_t st) {
     if (n == 0) return;

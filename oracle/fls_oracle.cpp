@@ -48,6 +48,8 @@ struct Reg {
     std::unique_ptr<LoamP2PlaneIvox> p2p;
     std::unique_ptr<IncrementalNdt> ndt;
     std::unique_ptr<IcpOptimized> icp;
+    std::unique_ptr<LoamP2PlaneKdtree> kd;
+    std::unique_ptr<LoamFull> full;
     MatchResult last;
 };
 
@@ -156,6 +158,17 @@ void* orc_reg_create(const fls_config* c) {
                                           c->source_cloud_filter_size, c->icp_max_correspond_distance, c->position_converge_thres,
                                           c->rotation_converge_thres, c->rot_thre_add_cloud, c->dist_thre_add_cloud, c->localization_mode != 0));
             break;
+        case FLS_P2PLANE_KNN:
+            r->kd.reset(new LoamP2PlaneKdtree(c->point_to_planar_thres, c->position_converge_thres, c->rotation_converge_thres,
+                                              c->rot_thre_add_cloud, c->dist_thre_add_cloud, unsigned(c->local_map_size), c->map_cloud_filter_size,
+                                              unsigned(c->max_iterations), c->localization_mode != 0));
+            break;
+        case FLS_LOAM_FULL:
+            r->full.reset(new LoamFull(c->point_to_planar_thres, c->point_search_thres, c->line_ratio_thres, c->position_converge_thres,
+                                       c->rotation_converge_thres, c->dist_thre_add_cloud, c->rot_thre_add_cloud,
+                                       unsigned(c->corner_local_map_size), unsigned(c->local_map_size), c->corner_map_filter_size,
+                                       c->map_cloud_filter_size, unsigned(c->max_iterations)));
+            break;
         default:
             delete r;
             return nullptr;
@@ -170,6 +183,14 @@ int orc_reg_add_cloud(void* h, const void* pts, size_t n, size_t stride) {
     if (r->p2p) r->p2p->add_cloud(c);
     else if (r->ndt) r->ndt->add_cloud(c);
     else if (r->icp) r->icp->add_cloud(c);
+    else if (r->kd) r->kd->add_cloud(c);
+    else return -1;  // LoamFull takes {planar, corner}: orc_reg_add_cloud2
+    return 0;
+}
+int orc_reg_add_cloud2(void* h, const void* planar, size_t n_planar, const void* corner, size_t n_corner, size_t stride) {
+    auto* r = static_cast<Reg*>(h);
+    if (!r->full) return -1;
+    r->full->add_cloud(load_cloud(planar, n_planar, stride), load_cloud(corner, n_corner, stride));
     return 0;
 }
 
@@ -182,7 +203,9 @@ int orc_reg_match(void* h, const void* pts, size_t n, size_t stride, double* T_c
     const auto t0 = std::chrono::steady_clock::now();
     if (r->p2p) r->last = r->p2p->match(c, T);
     else if (r->ndt) r->last = r->ndt->match(c, T);
-    else r->last = r->icp->match(c, T);
+    else if (r->icp) r->last = r->icp->match(c, T);
+    else if (r->kd) r->last = r->kd->match(c, T);
+    else return -1;
     const auto t1 = std::chrono::steady_clock::now();
     row2col(T, T_col);
     if (converged) *converged = r->last.converged ? 1 : 0;
@@ -193,6 +216,30 @@ int orc_reg_match(void* h, const void* pts, size_t n, size_t stride, double* T_c
         st->n_valid = r->last.n_valid;
         st->sum_residual = r->last.sum_res;
         st->n_source = int64_t(n);
+    }
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    return 0;
+}
+// LoamFull: {planar, corner} feature clouds of one scan
+int orc_reg_match2(void* h, const void* planar, size_t n_planar, const void* corner, size_t n_corner, size_t stride, double* T_col, int* converged,
+                   fls_match_stats* st, double* seconds) {
+    auto* r = static_cast<Reg*>(h);
+    if (!r->full) return -1;
+    const Cloud cp = load_cloud(planar, n_planar, stride), cc = load_cloud(corner, n_corner, stride);
+    double T[16];
+    col2row(T_col, T);
+    const auto t0 = std::chrono::steady_clock::now();
+    r->last = r->full->match(cp, cc, T);
+    const auto t1 = std::chrono::steady_clock::now();
+    row2col(T, T_col);
+    if (converged) *converged = r->last.converged ? 1 : 0;
+    if (st) {
+        std::memset(st, 0, sizeof(*st));
+        st->iterations = r->last.iters;
+        st->converged = r->last.converged;
+        st->n_valid = r->last.n_valid;
+        st->sum_residual = r->last.sum_res;
+        st->n_source = int64_t(n_planar + n_corner);
     }
     if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
     return 0;
@@ -213,19 +260,37 @@ float orc_reg_fitness(void* h, float max_range) {
     auto* r = static_cast<Reg*>(h);
     if (r->p2p) return r->p2p->fitness(max_range);
     if (r->ndt) return r->ndt->fitness(max_range);
+    if (r->kd) return r->kd->fitness(max_range);
+    if (r->full) return r->full->fitness(max_range);
     return r->icp->fitness(max_range);
 }
 size_t orc_reg_map_voxels(void* h) {
     auto* r = static_cast<Reg*>(h);
     if (r->p2p) return r->p2p->ivox().num_voxels();
     if (r->ndt) return r->ndt->num_voxels();
+    if (r->kd) return r->kd->map().size();
+    if (r->full) return r->full->planar_map().size();
     return r->icp->map().size();
 }
 size_t orc_reg_map_points(void* h) {
     auto* r = static_cast<Reg*>(h);
     if (r->p2p) return r->p2p->ivox().num_points();
     if (r->icp) return r->icp->map().size();
+    if (r->kd) return r->kd->map().size();
+    if (r->full) return r->full->planar_map().size() + r->full->corner_map().size();
     return 0;
+}
+// copies the current local map (kd-tree plug-ins / ICP) into out (capacity cap points, packed xyzi); which = 0 planar / only map, 1 = corner map
+size_t orc_reg_map_copy(void* h, int which, float* out, size_t cap) {
+    auto* r = static_cast<Reg*>(h);
+    const Cloud* m = nullptr;
+    if (r->icp) m = &r->icp->map();
+    else if (r->kd) m = &r->kd->map();
+    else if (r->full) m = which ? &r->full->corner_map() : &r->full->planar_map();
+    if (!m) return 0;
+    const size_t n = std::min(cap, m->size());
+    std::memcpy(out, m->data(), n * sizeof(P4));
+    return m->size();
 }
 // NDT voxel dump: returns count; arrays sized by orc_reg_map_voxels
 size_t orc_reg_ndt_dump(void* h, int* keys, double* mu, double* info, int* est) {

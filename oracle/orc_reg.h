@@ -5,6 +5,8 @@
 //   LoamP2PlaneIvox  <- include/registration/loam_point_to_plane_ivox.h:30-369  (Type=double)
 //   IncrementalNdt   <- include/registration/incremental_ndt.h:16-398
 //   IcpOptimized     <- include/registration/icp_optimized.h:15-253            (Type=double)
+//   LoamP2PlaneKdtree<- include/registration/loam_point_to_plane_kdtree.h:24-322 (Type=double)
+//   LoamFull         <- include/registration/loam_full_kdtree.h:24-435          (Type=double)
 // Structure kept deliberately close to upstream so that timing it is representative of the CPU
 // path: parallel per-point loop (OpenMP here, TBB std::execution::par upstream), SERIAL H/g
 // summation, per-iteration allocation of the per-point buffers, fp64 maths on fp32 points.
@@ -634,6 +636,325 @@ private:
     std::deque<Cloud> deque_;
     Cloud map_, src_;
     ExactKnn tree_;
+};
+
+
+// =================================================================================================
+// Shared pieces of the kd-tree LOAM plug-ins.
+
+// rigid key-frame gate shared by LoamPointToPlaneKdtree / LoamFull (loam_point_to_plane_kdtree.h:186-202,
+// loam_full_kdtree.h:356-371): `static last_T = T` on the first call  [quirk 7]
+struct KeyframeGate {
+    bool have_last = false;
+    double lastT[16];
+    bool need(const double* T, double dist_add, double rot_add) {
+        if (!have_last) { std::memcpy(lastT, T, sizeof(lastT)); have_last = true; }
+        double Rl[9], tl[3], R[9], t[3], Rli[9], Rd[9], rpy[3];
+        T_get_Rt(lastT, Rl, tl);
+        T_get_Rt(T, R, t);
+        inv3(Rl, Rli);
+        mat3_mul(Rli, R, Rd);
+        rot_to_rpy(Rd, rpy);
+        const double dt[3] = {t[0] - tl[0], t[1] - tl[1], t[2] - tl[2]};
+        if (norm3(dt) > dist_add || std::fabs(rpy[0]) > rot_add || std::fabs(rpy[1]) > rot_add || std::fabs(rpy[2]) > rot_add) {
+            std::memcpy(lastT, T, sizeof(lastT));
+            return true;
+        }
+        return false;
+    }
+};
+
+// plane through 5 neighbours -> J (6), |d|; false when the point is rejected
+// (loam_point_to_plane_kdtree.h:226-283 == loam_full_kdtree.h:295-343 == loam_point_to_plane_ivox.h:275-321)
+inline bool plane_term(const P4* nn, const P4& sp, const P4& q, const double* R, double thr, double* J, double* ad) {
+    double A[15];
+    const double b[5] = {-1, -1, -1, -1, -1};
+    for (int j = 0; j < 5; ++j) { A[j * 3 + 0] = nn[j].x; A[j * 3 + 1] = nn[j].y; A[j * 3 + 2] = nn[j].z; }
+    double c[3];
+    lstsq_colpiv_qr<5, 3>(A, b, c);
+    const double cn = norm3(c);
+    for (int j = 0; j < 5; ++j)
+        if (std::fabs(dot3(A + j * 3, c) + 1.0) / cn > thr) return false;
+    const double n[3] = {c[0] / cn, c[1] / cn, c[2] / cn};
+    const double ps[3] = {double(sp.x), double(sp.y), double(sp.z)};
+    const double pt[3] = {double(q.x) - A[0], double(q.y) - A[1], double(q.z) - A[2]};
+    const double d = dot3(pt, n);  // measured from the NEAREST neighbour  [quirk 2]
+    if (norm3(ps) < 81 * d * d) return false;  // body-frame norm  [quirk 3]
+    const double s = d > 0 ? 1.0 : -1.0;
+    double Rp[3];
+    mat3_vec(R, ps, Rp);
+    cross3(Rp, n, J);
+    for (int a = 0; a < 3; ++a) { J[a] *= s; J[3 + a] = n[a] * s; }
+    *ad = std::fabs(d);
+    return true;
+}
+
+// per-class persistent H_i / g_i / res_i / flag arrays with the "reset once per Match" rule  [quirk 1]
+struct TermStore {
+    std::vector<double> Hc, gc, res;
+    std::vector<uint8_t> flags;
+    void reset(size_t N) { Hc.resize(N * 36); gc.resize(N * 6); res.resize(N); flags.assign(N, 0); }
+    void set(size_t i, const double* J, double r) {
+        flags[i] = 1;
+        for (int a = 0; a < 6; ++a) {
+            for (int b = 0; b < 6; ++b) Hc[i * 36 + a * 6 + b] = J[a] * J[b];
+            gc[i * 6 + a] = -J[a] * r;
+        }
+        res[i] = r;
+    }
+    // serial sum over all flagged points, stale ones included; returns the count
+    size_t sum_into(IterLog& lg, double& sum_res) const {
+        size_t n = 0;
+        sum_res = 0;
+        for (size_t i = 0; i < flags.size(); ++i) {
+            if (!flags[i]) continue;
+            ++n;
+            for (int k = 0; k < 36; ++k) lg.H[k] += Hc[i * 36 + k];
+            for (int k = 0; k < 6; ++k) lg.g[k] += gc[i * 6 + k];
+            sum_res += res[i];
+        }
+        return n;
+    }
+};
+
+// one LOAM Gauss-Newton update + stop rule (loam_point_to_plane_kdtree.h:108-136, loam_full_kdtree.h:136-170)
+inline bool loam_gn_update(IterLog& lg, double* T_, double& last_rot, double& last_pos, double rot_thres, double pos_thres) {
+    solve_fullpiv<6>(lg.H, lg.g, lg.dx);
+    double Rd[9], R[9], t[3], Rn[9];
+    so3_exp(lg.dx, Rd);
+    T_get_Rt(T_, R, t);
+    mat3_mul(Rd, R, Rn);
+    T_set_R(T_, Rn);
+    for (int a = 0; a < 3; ++a) T_[a * 4 + 3] += lg.dx[3 + a];
+    const double rn = norm3(lg.dx), pn = norm3(lg.dx + 3);
+    const double drot = std::fabs(rn - last_rot), dpos = std::fabs(pn - last_pos);
+    last_rot = rn;
+    last_pos = pn;
+    return (rn < rot_thres && pn < pos_thres) || (drot < 1.0e-4 && dpos < 1.0e-4);
+}
+
+// =================================================================================================
+// LoamPointToPlaneKdtree<double>  (include/registration/loam_point_to_plane_kdtree.h:24-322)
+class LoamP2PlaneKdtree {
+public:
+    LoamP2PlaneKdtree(double plane_thres, double pos_thres, double rot_thres, double rot_add, double dist_add, unsigned local_map_size,
+                      float map_leaf, unsigned iters, bool localization)
+        : plane_thres_(plane_thres), pos_thres_(pos_thres), rot_thres_(rot_thres), rot_add_(rot_add), dist_add_(dist_add),
+          local_map_size_(local_map_size), map_leaf_(map_leaf), iters_(iters), loc_(localization) {}
+
+    // :56-80 — the per-cloud down-sample inside the loop is computed and discarded upstream (:73)
+    void add_cloud(const Cloud& planar) {
+        Cloud merged;
+        if (loc_) {
+            merged = planar;
+        } else {
+            deque_.push_back(planar);
+            if (deque_.size() > local_map_size_) deque_.pop_front();
+            for (const Cloud& it : deque_) merged.insert(merged.end(), it.begin(), it.end());
+        }
+        map_ = voxel_grid(merged, map_leaf_);  // :78
+        tree_.build(map_);
+    }
+
+    // :82-157
+    MatchResult match(const Cloud& planar, double* T) {
+        MatchResult res;
+        src_ = planar;
+        const size_t N = planar.size();
+        store_.reset(N);  // :98 flags reset once per Match  [quirk 1]
+        std::memcpy(T_, T, sizeof(T_));
+        double last_rot = 0.0, last_pos = 0.0;
+        size_t n_valid = 0;
+        double sum_res = 0;
+        for (unsigned it = 0; it < iters_; ++it) {
+            double R[9], t[3];
+            T_get_Rt(T_, R, t);
+#pragma omp parallel for schedule(dynamic, 256)
+            for (int64_t ii = 0; ii < int64_t(N); ++ii) {
+                const size_t i = size_t(ii);
+                const P4 q = transform_point_d(planar[i], T_);  // :211-212
+                int idx[5];
+                float d2[5];
+                if (tree_.search(q, 5, idx, d2) < 5) continue;  // :217-221
+                P4 nn[5];
+                for (int j = 0; j < 5; ++j) nn[j] = tree_.point(idx[j]);
+                double J[6], ad;
+                if (plane_term(nn, planar[i], q, R, plane_thres_, J, &ad)) store_.set(i, J, ad);
+            }
+            IterLog lg{};
+            n_valid = store_.sum_into(lg, sum_res);
+            lg.n_valid = int64_t(n_valid);
+            lg.sum_res = sum_res;
+            const bool stop = loam_gn_update(lg, T_, last_rot, last_pos, rot_thres_, pos_thres_);
+            res.log.push_back(lg);
+            res.iters = int(it) + 1;
+            if (stop) break;
+        }
+        std::memcpy(T, T_, sizeof(T_));  // :139
+        std::memcpy(Tfinal_, T_, sizeof(T_));
+        const bool ok = n_valid >= 50u;  // :142-144
+        // :146-150 — IsNeedAddCloud is evaluated (and moves last_T) before the mode test
+        if (ok && gate_.need(T_, dist_add_, rot_add_) && !loc_) add_cloud(transform_cloud_f(src_, T_));
+        res.converged = ok;
+        res.n_valid = int64_t(n_valid);
+        res.sum_res = sum_res;
+        return res;
+    }
+
+    float fitness(float max_range) const { return fitness_score(tree_, src_, Tfinal_, max_range); }  // :159-183
+    const Cloud& map() const { return map_; }
+
+private:
+    double plane_thres_, pos_thres_, rot_thres_, rot_add_, dist_add_;
+    unsigned local_map_size_;
+    float map_leaf_;
+    unsigned iters_;
+    bool loc_;
+    KeyframeGate gate_;
+    double T_[16], Tfinal_[16];
+    std::deque<Cloud> deque_;
+    Cloud map_, src_;
+    ExactKnn tree_;
+    TermStore store_;
+};
+
+// =================================================================================================
+// LoamFull<double>  (include/registration/loam_full_kdtree.h:24-435)
+class LoamFull {
+public:
+    LoamFull(double plane_thres, double search_thres, double line_ratio, double pos_thres, double rot_thres, double dist_add, double rot_add,
+             unsigned local_corner_size, unsigned local_planar_size, float corner_leaf, float planar_leaf, unsigned iters)
+        : plane_thres_(plane_thres), search_thres_(search_thres), line_ratio_(line_ratio), pos_thres_(pos_thres), rot_thres_(rot_thres),
+          dist_add_(dist_add), rot_add_(rot_add), local_corner_size_(local_corner_size), local_planar_size_(local_planar_size),
+          corner_leaf_(corner_leaf), planar_leaf_(planar_leaf), iters_(iters) {}
+
+    // :66-104 — {planar, corner}; the voxel filters only run once a deque holds more than 5 clouds
+    void add_cloud(const Cloud& planar, const Cloud& corner) {
+        corner_deque_.push_back(corner);
+        planar_deque_.push_back(planar);
+        if (planar_deque_.size() > local_planar_size_) planar_deque_.pop_front();
+        if (corner_deque_.size() > local_corner_size_) corner_deque_.pop_front();
+        planar_map_.clear();
+        corner_map_.clear();
+        for (const Cloud& c : planar_deque_) planar_map_.insert(planar_map_.end(), c.begin(), c.end());
+        for (const Cloud& c : corner_deque_) corner_map_.insert(corner_map_.end(), c.begin(), c.end());
+        if (planar_deque_.size() > 5) planar_map_ = voxel_grid(planar_map_, planar_leaf_);
+        if (corner_deque_.size() > 5) corner_map_ = voxel_grid(corner_map_, corner_leaf_);
+        planar_tree_.build(planar_map_);
+        corner_tree_.build(corner_map_);
+    }
+
+    // :106-204
+    MatchResult match(const Cloud& planar, const Cloud& corner, double* T) {
+        MatchResult res;
+        const size_t Nc = corner.size(), Np = planar.size();
+        cstore_.reset(Nc);
+        pstore_.reset(Np);
+        std::memcpy(T_, T, sizeof(T_));
+        double last_rot = 0.0, last_pos = 0.0;
+        size_t nv_c = 0, nv_p = 0;
+        double res_c = 0, res_p = 0;
+        for (unsigned it = 0; it < iters_; ++it) {
+            double R[9], t[3];
+            T_get_Rt(T_, R, t);
+            // CornerMatch :211-273
+#pragma omp parallel for schedule(dynamic, 64)
+            for (int64_t ii = 0; ii < int64_t(Nc); ++ii) {
+                const size_t i = size_t(ii);
+                const P4 q = transform_point_d(corner[i], T_);
+                int idx[5];
+                float d2[5];
+                if (corner_tree_.search(q, 5, idx, d2) < 5) continue;  // upstream reads 5 indices unconditionally
+                if (double(d2[4]) > search_thres_) continue;           // :227
+                double P[15], c[3] = {0, 0, 0};
+                for (int j = 0; j < 5; ++j) {
+                    const P4& m = corner_tree_.point(idx[j]);
+                    P[j * 3 + 0] = m.x; P[j * 3 + 1] = m.y; P[j * 3 + 2] = m.z;
+                    for (int a = 0; a < 3; ++a) c[a] += P[j * 3 + a];
+                }
+                for (int a = 0; a < 3; ++a) c[a] /= 5.0;  // rowwise().mean()
+                double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                for (int j = 0; j < 5; ++j)
+                    for (int a = 0; a < 3; ++a)
+                        for (int b = 0; b < 3; ++b) S[a * 3 + b] += (P[j * 3 + a] - c[a]) * (P[j * 3 + b] - c[b]);
+                for (int k = 0; k < 9; ++k) S[k] /= 5.0;  // :239-242
+                double lam[3], V[9];
+                sym_eig3(S, lam, V);  // JacobiSVD of a symmetric PSD matrix (:244)
+                if (lam[0] <= line_ratio_ * lam[1]) continue;  // :249
+                const double n[3] = {V[0], V[3], V[6]};        // V.col(0); J is invariant to its sign
+                const double ps[3] = {double(corner[i].x), double(corner[i].y), double(corner[i].z)};
+                const double v[3] = {double(q.x) - c[0], double(q.y) - c[1], double(q.z) - c[2]};
+                double w[3];
+                cross3(v, n, w);
+                const double d = norm3(w);  // :260
+                const double u[3] = {w[0] / d, w[1] / d, w[2] / d};
+                // J.head = (n^ (Rp)^)^T u = (Rp)^T^ n^T^ u ... evaluated literally: M = n^ * (Rp)^ ; J.head = M^T u   (:264)
+                double Rp[3], Nh[9], Ph[9], M[9], J[6];
+                mat3_vec(R, ps, Rp);
+                so3_hat(n, Nh);
+                so3_hat(Rp, Ph);
+                mat3_mul(Nh, Ph, M);
+                for (int a = 0; a < 3; ++a) J[a] = M[0 * 3 + a] * u[0] + M[1 * 3 + a] * u[1] + M[2 * 3 + a] * u[2];
+                // J.tail = (-n^)^T u = n^ u = n x u   (:265)
+                cross3(n, u, J + 3);
+                cstore_.set(i, J, d);  // g = -J d, res = d  (:267-270)
+            }
+            // PlanarMatch :275-345
+#pragma omp parallel for schedule(dynamic, 256)
+            for (int64_t ii = 0; ii < int64_t(Np); ++ii) {
+                const size_t i = size_t(ii);
+                const P4 q = transform_point_d(planar[i], T_);
+                int idx[5];
+                float d2[5];
+                if (planar_tree_.search(q, 5, idx, d2) < 5) continue;
+                if (double(d2[4]) > search_thres_) continue;  // :291
+                P4 nn[5];
+                for (int j = 0; j < 5; ++j) nn[j] = planar_tree_.point(idx[j]);
+                double J[6], ad;
+                if (plane_term(nn, planar[i], q, R, plane_thres_, J, &ad)) pstore_.set(i, J, ad);
+            }
+            IterLog lg{};
+            nv_c = cstore_.sum_into(lg, res_c);  // :347-372 corners first
+            nv_p = pstore_.sum_into(lg, res_p);
+            lg.n_valid = int64_t(nv_p);
+            lg.sum_res = res_p + res_c;
+            const bool stop = loam_gn_update(lg, T_, last_rot, last_pos, rot_thres_, pos_thres_);
+            res.log.push_back(lg);
+            res.iters = int(it) + 1;
+            if (stop) break;
+        }
+        std::memcpy(T, T_, sizeof(T_));  // :172
+        const bool ok = nv_p >= 50;      // :174-176 planar count only
+        if (ok && gate_.need(T_, dist_add_, rot_add_)) {  // :178-186 pcl::transformPointCloud with the double matrix
+            Cloud tp(planar.size()), tc(corner.size());
+            for (size_t i = 0; i < planar.size(); ++i) tp[i] = transform_point_d(planar[i], T_);
+            for (size_t i = 0; i < corner.size(); ++i) tc[i] = transform_point_d(corner[i], T_);
+            add_cloud(tp, tc);
+        }
+        res.converged = ok;
+        res.n_valid = int64_t(nv_p);
+        res.sum_res = res_p + res_c;
+        n_valid_corner_ = nv_c;
+        return res;
+    }
+
+    float fitness(float) const { return std::numeric_limits<float>::max(); }  // :206-208 FloatNaN
+    const Cloud& planar_map() const { return planar_map_; }
+    const Cloud& corner_map() const { return corner_map_; }
+    size_t n_valid_corner() const { return n_valid_corner_; }
+
+private:
+    double plane_thres_, search_thres_, line_ratio_, pos_thres_, rot_thres_, dist_add_, rot_add_;
+    unsigned local_corner_size_, local_planar_size_;
+    float corner_leaf_, planar_leaf_;
+    unsigned iters_;
+    KeyframeGate gate_;
+    double T_[16];
+    std::deque<Cloud> corner_deque_, planar_deque_;
+    Cloud corner_map_, planar_map_;
+    ExactKnn corner_tree_, planar_tree_;
+    TermStore cstore_, pstore_;
+    size_t n_valid_corner_ = 0;
 };
 
 }  // namespace orc

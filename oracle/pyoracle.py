@@ -59,6 +59,10 @@ def lib():
         L.orc_reg_add_cloud.argtypes = [vp, vp, sz, sz]
         L.orc_reg_match.argtypes = [vp, vp, sz, sz, vp, C.POINTER(i32), C.POINTER(FlsMatchStats), C.POINTER(dbl)]
         L.orc_reg_get_iter_log.argtypes = [vp, C.POINTER(FlsIterLog), i32]
+        L.orc_reg_add_cloud2.argtypes = [vp, vp, sz, vp, sz, sz]
+        L.orc_reg_match2.argtypes = [vp, vp, sz, vp, sz, sz, vp, C.POINTER(i32), C.POINTER(FlsMatchStats), C.POINTER(dbl)]
+        L.orc_reg_map_copy.restype = sz
+        L.orc_reg_map_copy.argtypes = [vp, i32, vp, sz]
         L.orc_reg_fitness.restype = f32
         L.orc_reg_fitness.argtypes = [vp, f32]
         L.orc_reg_map_voxels.restype = sz
@@ -231,19 +235,39 @@ class Registration:
             raise ValueError(f"oracle does not implement method {cfg.method}")
         self.last_seconds = 0.0
 
-    def add_cloud(self, pts):
+    def add_cloud(self, pts, corner=None):
+        """One cloud for ICP / NDT / point-to-plane; (planar, corner) for LoamFull."""
         pts = _f4(pts)
-        lib().orc_reg_add_cloud(self._h, _p(pts), len(pts), 16)
+        if corner is not None:
+            corner = _f4(corner)
+            rc = lib().orc_reg_add_cloud2(self._h, _p(pts), len(pts), _p(corner), len(corner), 16)
+        else:
+            rc = lib().orc_reg_add_cloud(self._h, _p(pts), len(pts), 16)
+        if rc != 0:
+            raise ValueError("wrong number of clouds for this plug-in")
 
-    def match(self, pts, T):
+    def match(self, pts, T, corner=None):
         pts = _f4(pts)
         Tc = np.ascontiguousarray(np.asarray(T, np.float64).T).copy()
         conv = C.c_int(0)
         st = FlsMatchStats()
         sec = C.c_double(0)
-        lib().orc_reg_match(self._h, _p(pts), len(pts), 16, _p(Tc), C.byref(conv), C.byref(st), C.byref(sec))
+        if corner is not None:
+            corner = _f4(corner)
+            rc = lib().orc_reg_match2(self._h, _p(pts), len(pts), _p(corner), len(corner), 16, _p(Tc), C.byref(conv), C.byref(st), C.byref(sec))
+        else:
+            rc = lib().orc_reg_match(self._h, _p(pts), len(pts), 16, _p(Tc), C.byref(conv), C.byref(st), C.byref(sec))
+        if rc != 0:
+            raise ValueError("wrong number of clouds for this plug-in")
         self.last_seconds = sec.value
         return bool(conv.value), Tc.T.copy(), st
+
+    def map_copy(self, which=0):
+        """Current local map of the kd-tree plug-ins / ICP (which=1: LoamFull's corner map)."""
+        n = lib().orc_reg_map_copy(self._h, int(which), None, 0)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        lib().orc_reg_map_copy(self._h, int(which), _p(out), n)
+        return out[:n]
 
     def iter_log(self, cap=64):
         buf = (FlsIterLog * cap)()
