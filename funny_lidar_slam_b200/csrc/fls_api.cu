@@ -222,7 +222,23 @@ int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* co
     fused_loop = true;
     last_src = d_src;
     last_src_n = n;
-    return finish_match(T, converged, st, (long long)n);
+    const int rc = finish_match(T, converged, st, (long long)n);
+    if (rc != FLS_OK) return rc;
+    if (h_state->converged && !cfg.localization_mode) {
+        // :205-206 — the scan enters the map through the cached-5-NN rule (body-frame points, final pose)  [quirk 8]
+        stage.reserve(n + 1);
+        stage2.reserve(n + 1);
+        const GnState& s = *h_state;
+        const size_t n_add = select_ivox_inserts(ivox_view(), d_src, ni, s.Rprev, s.tprev, s.R, s.t, 0.5 /* filter_size_map_min_ (:351) */,
+                                                 stage2.p, stage.p, scratch, stream, &launches);
+        const int rc2 = ivox.append_and_build(stage.p, n_add, cfg.ivox_capacity, stream);
+        launches += ivox.launches;
+        ivox.launches = 0;
+        FLS_CUDA(cudaStreamSynchronize(stream));
+        if (st) st->gpu_launches = launches;
+        if (rc2 != FLS_OK) return rc2;
+    }
+    return FLS_OK;
 }
 
 // ---- IncrementalNDT ----------------------------------------------------------------------------------------------

@@ -37,6 +37,9 @@ size_t p2plane_partials_len(int n);   // doubles in the partial-sum buffer (chun
 void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st);
 void prepare_queries(const float4* d_src, int n, const double* T_colmajor, GnState* d_state, float inv_res, unsigned char* d_flags, int* d_sync,
                      int n_sync, float4* d_sorted, BuildScratch& sc, cudaStream_t st, int* launches);
+// LOAM-iVox Match-internal AddCloudToLocalMap: classify + compact the points that enter the map (d_world, d_out: n records)
+size_t select_ivox_inserts(const IvoxView& map, const float4* d_src, int n, const double* R_prev, const double* t_prev, const double* R_fin,
+                           const double* t_fin, double filter, float4* d_world, float4* d_out, BuildScratch& sc, cudaStream_t st, int* launches);
 void launch_ivox_knn_test(const IvoxView& map, const float4* d_q, int n, float4* d_out, int* d_found, cudaStream_t st);
 
 struct NdtArgs {

@@ -424,6 +424,71 @@ __global__ void ivox_knn_test_kernel(IvoxView map, const float4* __restrict__ q,
     found[i] = f;
 }
 
+// LoamPointToPlaneIVOX::AddCloudToLocalMap, the Match-internal call (loam_point_to_plane_ivox.h:79-128 upstream): every
+// body-frame point is moved to the map with the FINAL pose and then kept or dropped by looking at the 5 neighbours its
+// last PlanerMatch found (those were searched at the pose BEFORE the last update — GnState::Rprev/tprev) and at the
+// centre of the 0.5 m cell it falls into:  class 2 ("no need to down-sample": nearest neighbour outside the cell in all
+// three axes), class 1 (no cached neighbour closer to the cell centre than the point itself), class 0 (dropped)  [quirk 8].
+__global__ void ivox_insert_rule_kernel(IvoxView map, const float4* __restrict__ src, int n, PoseArg prev, PoseArg fin, double filter,
+                                        unsigned char* __restrict__ cls, float4* __restrict__ world) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 sp = src[i];
+    const float qx = xform_row_d(prev.R[0], prev.R[1], prev.R[2], prev.t[0], (double)sp.x, (double)sp.y, (double)sp.z);
+    const float qy = xform_row_d(prev.R[3], prev.R[4], prev.R[5], prev.t[1], (double)sp.x, (double)sp.y, (double)sp.z);
+    const float qz = xform_row_d(prev.R[6], prev.R[7], prev.R[8], prev.t[2], (double)sp.x, (double)sp.y, (double)sp.z);
+    Top5 nn;
+    unsigned nc;
+    knn5_stream(map, qx, qy, qz, nn, nc);
+    const float wx = xform_row_d(fin.R[0], fin.R[1], fin.R[2], fin.t[0], (double)sp.x, (double)sp.y, (double)sp.z);
+    const float wy = xform_row_d(fin.R[3], fin.R[4], fin.R[5], fin.t[1], (double)sp.x, (double)sp.y, (double)sp.z);
+    const float wz = xform_row_d(fin.R[6], fin.R[7], fin.R[8], fin.t[2], (double)sp.x, (double)sp.y, (double)sp.z);
+    world[i] = make_float4(wx, wy, wz, sp.w);
+    const unsigned js[5] = {nn.k0, nn.k1, nn.k2, nn.k3, nn.k4};
+    if (js[0] == 0xffffffffu) {  // no cached neighbour at all (:93-96)
+        cls[i] = 1;
+        return;
+    }
+    const double pv[3] = {(double)wx, (double)wy, (double)wz};
+    double c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) c[a] = (floor(pv[a] / filter) + 0.5) * filter;  // :97-99
+    const float4 n0 = __ldg(map.lists + js[0]);
+    const double half = 0.5 * filter;
+    if (fabs((double)n0.x - c[0]) > half && fabs((double)n0.y - c[1]) > half && fabs((double)n0.z - c[2]) > half) {  // :103-108
+        cls[i] = 2;
+        return;
+    }
+    bool need = true;
+    const double dist = (pv[0] - c[0]) * (pv[0] - c[0]) + (pv[1] - c[1]) * (pv[1] - c[1]) + (pv[2] - c[2]) * (pv[2] - c[2]);
+    if (js[4] != 0xffffffffu) {  // NUM_MATCH_POINTS cached neighbours (:113)
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const float4 m = __ldg(map.lists + js[r]);
+            const double ex = (double)m.x - c[0], ey = (double)m.y - c[1], ez = (double)m.z - c[2];
+            if (ex * ex + ey * ey + ez * ez < dist + 1.0e-6) need = false;  // :114-120
+        }
+    }
+    cls[i] = need ? 1 : 0;
+}
+
+// stable two-class compaction: class-1 points first, then class-2 points, both in input order (:126-127)
+__global__ void ivox_insert_keys_kernel(const unsigned char* __restrict__ cls, int n, unsigned long long* __restrict__ ones) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ones[i] = (cls[i] == 1 ? 1ull : 0ull) | (cls[i] == 2 ? (1ull << 32) : 0ull);
+}
+__global__ void ivox_insert_scatter_kernel(const unsigned char* __restrict__ cls, const unsigned long long* __restrict__ excl, int n,
+                                           const float4* __restrict__ world, float4* __restrict__ out, unsigned long long* __restrict__ total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long last = excl[n - 1] + ((cls[n - 1] == 1 ? 1ull : 0ull) | (cls[n - 1] == 2 ? (1ull << 32) : 0ull));
+    const unsigned n1 = (unsigned)(last & 0xffffffffull);
+    if (i == 0) *total = last;
+    const unsigned char c = cls[i];
+    if (c == 1) out[(unsigned)(excl[i] & 0xffffffffull)] = world[i];
+    else if (c == 2) out[n1 + (unsigned)(excl[i] >> 32)] = world[i];
+}
+
 constexpr int kMinBlocks = 2;  // 2 x 384 threads: <= 80 registers, 24 warps / SM — enough resident warps to cover a 100k-point scan in one pass
 
 }  // namespace
@@ -492,6 +557,40 @@ void prepare_queries(const float4* d_src, int n, const double* T_colmajor, GnSta
     FLS_CUDA(cub::DeviceRadixSort::SortPairs(sc.cub_tmp.p, tb, sc.k32a.p, sc.k32b.p, sc.idx.p, sc.idx_sorted.p, n, 0, key_bits, st));
     gather4_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_src, sc.idx_sorted.p, n, d_sorted);
     if (launches) *launches += 2 + key_bits / 8 + 1;
+}
+
+// Returns the number of points selected for insertion (class 1 then class 2, input order) in d_out; synchronises the stream.
+size_t select_ivox_inserts(const IvoxView& map, const float4* d_src, int n, const double* R_prev, const double* t_prev, const double* R_fin,
+                           const double* t_fin, double filter, float4* d_world, float4* d_out, BuildScratch& sc, cudaStream_t st, int* launches) {
+    if (n <= 0) return 0;
+    PoseArg prev, fin;
+    for (int k = 0; k < 9; ++k) {
+        prev.R[k] = R_prev[k];
+        fin.R[k] = R_fin[k];
+    }
+    for (int k = 0; k < 3; ++k) {
+        prev.t[k] = t_prev[k];
+        fin.t[k] = t_fin[k];
+    }
+    sc.minmax.reserve((size_t)n / 4 + 16);  // class bytes
+    unsigned char* cls = reinterpret_cast<unsigned char*>(sc.minmax.p);
+    sc.keys.reserve((size_t)n + 1);
+    sc.keys_sorted.reserve((size_t)n + 1);
+    const int g = (n + 127) / 128;
+    ivox_insert_rule_kernel<<<g, 128, 0, st>>>(map, d_src, n, prev, fin, filter, cls, d_world);
+    ivox_insert_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(cls, n, sc.keys.p);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, sc.keys.p, sc.keys_sorted.p, n, st);
+    sc.cub_tmp.reserve(tb + 256);
+    tb = sc.cub_tmp.cap;
+    FLS_CUDA(cub::DeviceScan::ExclusiveSum(sc.cub_tmp.p, tb, sc.keys.p, sc.keys_sorted.p, n, st));
+    unsigned long long* d_total = sc.keys.p + n;  // spare slot
+    ivox_insert_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(cls, sc.keys_sorted.p, n, d_world, d_out, d_total);
+    unsigned long long total = 0;
+    FLS_CUDA(cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, st));
+    FLS_CUDA(cudaStreamSynchronize(st));
+    if (launches) *launches += 4;
+    return (size_t)(total & 0xffffffffull) + (size_t)(total >> 32);
 }
 
 void launch_ivox_knn_test(const IvoxView& map, const float4* d_q, int n, float4* d_out, int* d_found, cudaStream_t st) {

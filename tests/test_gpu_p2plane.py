@@ -119,3 +119,42 @@ def test_match_failure_paths(scene16):
     Tg = scene16["guess"].copy()
     assert g.Match(PointcloudCluster(planar_cloud=np.zeros((0, 4), np.float32)), Tg) is False
     assert np.allclose(Tg, scene16["guess"], atol=1e-12)
+
+
+def test_mapping_mode_stream(world, traj):
+    """Mapping mode (is_localization_mode=false): after every successful Match the scan enters the iVox map through the
+    cached-5-NN insertion rule (loam_point_to_plane_ivox.h:79-128 upstream, [quirk 8]); poses and map growth must
+    follow the oracle scan after scan."""
+    from funny_lidar_slam_b200.registration import PointcloudCluster, Registration
+    from oracle import pyoracle as orc
+    cfg = default_config(FLS_P2PLANE_IVOX, localization_mode=0, flags=FLS_FLAG_ITER_LOG)
+    g, o = Registration(cfg), orc.Registration(cfg)
+    first = synth.make_map_from_scans(world, traj[0:5:2], "vlp16", leaf=0.3)
+    g.AddCloudToLocalMap([first])
+    o.add_cloud(first)
+    assert g.map_info().n_points == o.map_points
+    grown = []
+    for k in range(1, 6):
+        scan = synth.voxel_downsample_np(synth.make_scan(world, traj[k], "vlp16", seed=40 + k)["points"], 0.4)
+        guess = synth.perturb_pose(traj[k], dpos=0.05, drot_deg=0.5, seed=k)
+        Tg = guess.copy()
+        ok_g = g.Match(PointcloudCluster(planar_cloud=scan), Tg)
+        ok_o, To, st_o = o.match(scan, guess)
+        assert ok_g and ok_o and g.last_stats.iterations == st_o.iterations, k
+        dt, dr = synth.pose_error(Tg, To)
+        assert dt < 1e-4 and dr < 1e-4, (k, dt, dr)
+        a, b = g.map_info().n_points, o.map_points
+        # the inserted points are transformed with poses that agree to ~1e-6 m: a point on a cell face or a tie in the
+        # "closer to the centre" test can flip, so sizes agree to a few points per scan, not bit for bit
+        assert abs(a - b) <= max(3, b // 5000), (k, a, b)
+        grown.append(b)
+    assert grown[-1] > grown[0] > len(first)
+
+
+def test_external_add_after_first_is_rejected_in_mapping_mode(scene16):
+    from funny_lidar_slam_b200._lib import FlsError
+    from funny_lidar_slam_b200.registration import Registration
+    g = Registration(default_config(FLS_P2PLANE_IVOX, localization_mode=0))
+    g.AddCloudToLocalMap([scene16["map"]])
+    with pytest.raises(FlsError):  # upstream would run the insertion rule on caches of a Match that never happened
+        g.AddCloudToLocalMap([scene16["map"]])
