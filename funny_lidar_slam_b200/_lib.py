@@ -14,7 +14,7 @@ _lib = None
 EXPORTS = [
     "fls_abi_version", "fls_device_count", "fls_last_error", "fls_strerror", "fls_config_default", "fls_create", "fls_destroy",
     "fls_add_cloud", "fls_match", "fls_match_device", "fls_fitness", "fls_get_iter_log", "fls_get_map_info", "fls_ivox_knn",
-    "fls_voxel_grid", "fls_extract_features",
+    "fls_voxel_grid", "fls_extract_features", "fls_project",
 ]
 
 

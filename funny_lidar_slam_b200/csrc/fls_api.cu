@@ -100,6 +100,13 @@ IvoxView Handle::grid_view(const IvoxMap& g) const {
     v.lists = g.lists.p;
     v.ctab = g.ctab.p;
     v.cmask = g.cmask;
+    // a query and a candidate of its stencil differ by at most 2*res per axis with a non-zero offset and res otherwise:
+    // d^2 <= 12 res^2 for the full 26-neighbourhood
+    {
+        const char* e = std::getenv("FLS_LIST_PREFETCH");
+        v.prefetch = e ? (unsigned)std::atoi(e) : 1u;
+    }
+    v.fast_knn = (12.0 * 1.01 * (double)g.res * (double)g.res < (double)v.max_range2 && !std::getenv("FLS_EXACT_KNN")) ? 1u : 0u;
     return v;
 }
 IvoxView Handle::ivox_view() const { return grid_view(ivox); }
@@ -174,14 +181,19 @@ int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* co
     rec1.reserve(n + 1);
     flags.reserve(n + 1);
     src_f.reserve(n + 1);
-    partials.reserve(p2plane_partials_len(ni));
-    // {next chunk, CTAs arrived} per iteration, the release flag, one self-resetting counter per chunk group
-    const size_t n_sync = 2 * (size_t)cfg.max_iterations + 1 + (size_t)p2plane_groups(ni) + 1;
-    sync_buf.reserve(n_sync);
-    // one prep kernel (state init, counter + flag reset, locality keys) + radix sort + gather: the queries end up in
-    // Morton order of the voxel they fall into at the initial pose (locality only: the sums are order-free up to fp64
-    // rounding, and the persistent per-point records live in the same order for the whole Match)
-    prepare_queries(d_src, ni, T, state.p, ivox.inv_res, flags.p, sync_buf.p, (int)n_sync, src_f.p, scratch, stream, &launches);
+    // hand-over buffers: one LL row per CTA + the LL pose record; tags are unique per (Match, iteration), so neither is
+    // ever cleared — only zeroed when (re)allocated, so that uninitialised memory cannot alias a tag
+    {
+        const size_t cap0 = ll_rows.cap;
+        ll_rows.reserve((size_t)grid * 32 + kLlPoseLen);
+        if (ll_rows.cap != cap0) FLS_CUDA(cudaMemsetAsync(ll_rows.p, 0, ll_rows.cap * sizeof(uint4), stream));
+    }
+    match_epoch = (match_epoch + 1) & 0xffffffu;
+    if (match_epoch == 0) match_epoch = 1;
+    // one prep kernel (state init, flag reset, locality keys) + radix sort + gather: the queries end up in Morton order of
+    // the voxel they fall into at the initial pose (locality only: the sums are order-free up to fp64 rounding, and the
+    // persistent per-point records live in the same order for the whole Match)
+    prepare_queries(d_src, ni, T, state.p, ivox_view(), flags.p, src_f.p, scratch, stream, &launches);
     P2PlaneLoopArgs a;
     a.src = src_f.p;
     a.n = ni;
@@ -191,17 +203,9 @@ int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* co
     a.rec0 = rec0.p;
     a.rec1 = rec1.p;
     a.flags = flags.p;
-    a.partials = partials.p;
-    a.sync = sync_buf.p;
-    a.sync_flag = sync_buf.p + 2 * (size_t)cfg.max_iterations;
-    a.dbg_cta = nullptr;
-    if (std::getenv("FLS_DEBUG_TIMING")) {
-        const size_t dbg_len = (size_t)grid * 4 * (1 + kP2PlaneBlock / 32);
-        dbg_cta.reserve(dbg_len);
-        FLS_CUDA(cudaMemsetAsync(dbg_cta.p, 0, dbg_len * sizeof(unsigned long long), stream));
-        a.dbg_cta = dbg_cta.p;
-        dbg_grid = grid;
-    }
+    a.rows = ll_rows.p;
+    a.ll_pose = ll_rows.p + (size_t)grid * 32;
+    a.tag_base = match_epoch << 8;
     a.gp.method = FLS_P2PLANE_IVOX;
     a.gp.max_iterations = cfg.max_iterations;
     a.gp.min_effective = 50;
@@ -580,43 +584,12 @@ int Handle::finish_match(double* T, int* converged, fls_match_stats* st, long lo
     }
     end_call(st);
     const GnState& s = *h_state;
-    if (fused_loop && std::getenv("FLS_DEBUG_TIMING") && dbg_grid > 0 && s.iter > 1) {
-        std::vector<unsigned long long> h((size_t)dbg_grid * 4 * (1 + kP2PlaneBlock / 32));
-        cudaMemcpy(h.data(), dbg_cta.p, h.size() * 8, cudaMemcpyDeviceToHost);
-        {
-            const int nw = dbg_grid * (kP2PlaneBlock / 32);
-            std::vector<int> order(nw);
-            for (int i = 0; i < nw; ++i) order[i] = i;
-            const unsigned long long* w = h.data() + (size_t)dbg_grid * 4;
-            std::sort(order.begin(), order.end(), [&](int x, int y) { return w[x * 4] < w[y * 4]; });
-            for (double q : {0.0, 0.25, 0.5, 0.75, 0.9, 0.99, 1.0}) {
-                const int k = order[(size_t)(q * (nw - 1))];
-                std::fprintf(stderr, "[fls timing] warp pct %.2f: point phase %llu cyc (knn %llu) | max list %llu, mean list %.1f\n", q, w[k * 4],
-                             w[k * 4 + 1], w[k * 4 + 2], w[k * 4 + 3] / 32.0);
-            }
-        }
-        const unsigned long long t0 = s.dbg[1][0];
-        std::vector<double> st, w0, wl, ar;
-        for (int b = 0; b < dbg_grid; ++b) {
-            st.push_back((double)(long long)(h[b * 4 + 0] - t0) * 1e-3);
-            w0.push_back((double)(long long)(h[b * 4 + 1] - t0) * 1e-3);
-            wl.push_back((double)(long long)(h[b * 4 + 2] - t0) * 1e-3);
-            ar.push_back((double)(long long)(h[b * 4 + 3] - t0) * 1e-3);
-        }
-        auto pct = [](std::vector<double> v, double q) {
-            std::sort(v.begin(), v.end());
-            return v[(size_t)(q * (v.size() - 1))];
-        };
-        std::fprintf(stderr, "[fls timing] it1 per-CTA (us from it start): start p0/50/100 %.1f %.1f %.1f | warp0 done %.1f %.1f %.1f | warpL done %.1f %.1f %.1f | cta done %.1f %.1f %.1f\n",
-                     pct(st, 0), pct(st, .5), pct(st, 1), pct(w0, 0), pct(w0, .5), pct(w0, 1), pct(wl, 0), pct(wl, .5), pct(wl, 1), pct(ar, 0),
-                     pct(ar, .5), pct(ar, 1));
-    }
     if (fused_loop && std::getenv("FLS_DEBUG_TIMING")) {
         std::fprintf(stderr, "[fls timing] iters %d  candidates/pt-iter %.1f  qr-fallback points/iter %.0f of %lld\n", s.iter,
                      s.cand_total / (double)(n_source * (s.iter > 0 ? s.iter : 1)), s.hits_total / (double)(s.iter > 0 ? s.iter : 1), n_source);
         for (int it = 0; it < s.iter && it < 16; ++it) {
             const unsigned long long* d = s.dbg[it];
-            std::fprintf(stderr, "[fls timing] it %d: work %.1f us | reduce %.1f us | solve %.1f us | to next start %.1f us\n", it,
+            std::fprintf(stderr, "[fls timing] it %d: until all rows in %.1f us | fold %.1f us | solve+publish %.1f us | to next start %.1f us\n", it,
                          (d[1] - d[0]) * 1e-3, (d[2] - d[1]) * 1e-3, (d[3] - d[2]) * 1e-3,
                          (it + 1 < s.iter && it + 1 < 16) ? (s.dbg[it + 1][0] - d[3]) * 1e-3 : 0.0);
         }
@@ -680,6 +653,17 @@ int fls_device_count(void) {
 }
 
 const char* fls_last_error(void) { return fls::last_error_cstr(); }
+
+int fls_project(int device, const void* raw, const int32_t* ring, size_t n, size_t stride, int32_t n_rows, int32_t n_cols, float horizontal_resolution,
+                float min_distance, float max_distance, float* ordered, float* depth, int32_t* col, int32_t* row_start, int32_t* row_end,
+                size_t* n_ordered) {
+    if ((!raw && n) || (!ring && n) || !ordered || !depth || !col || !row_start || !row_end || !n_ordered || !stride_ok(stride))
+        return FLS_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return FLS_ERR_NO_DEVICE;
+    return fls::project_device(device, raw, ring, n, stride, n_rows, n_cols, horizontal_resolution, min_distance, max_distance, ordered, depth, col,
+                               row_start, row_end, n_ordered);
+}
 
 const char* fls_strerror(int status) {
     switch (status) {
@@ -758,6 +742,7 @@ static int validate(const fls_config* c) {
     if (c->method == FLS_P2PLANE_IVOX) {
         if (!(c->point_to_planar_thres < 1e300) || !(c->ivox_resolution > 0.f)) return FLS_ERR_INVALID_ARG;
         if (c->ivox_k != 5) return FLS_ERR_UNSUPPORTED;  // upstream always asks for 5 (loam_point_to_plane_ivox.h:269)
+        if (c->max_iterations > 255) return FLS_ERR_UNSUPPORTED;  // 8-bit iteration field of the hand-over tags (fls_gn.cuh)
     } else if (c->method == FLS_NDT) {
         if (!(c->ndt_voxel_size > 0) || !(c->ndt_voxel_size < 1e300) || !(c->ndt_outlier_thres < 1e300) || !(c->source_cloud_filter_size > 0.f) ||
             c->ndt_capacity <= 0 || c->ndt_capacity == 2147483647 || c->ndt_min_points_in_voxel < 0 || c->ndt_min_points_in_voxel > 64)

@@ -60,19 +60,56 @@ __device__ __forceinline__ void block_reduce_store(double (&acc)[kNumAcc], doubl
     }
 }
 
+// ---- flag-in-data hand-over ("LL" records) ---------------------------------------------------------------------------
+// A 16-byte record {lo32, tag, hi32, tag} carries one double together with the tag of the iteration that produced it.
+// Each 8-byte half is a single-copy-atomic store, so a reader that sees the expected tag in BOTH halves has the value —
+// no fence before the store, no separate flag, no atomic: the latency of a hand-over is one store plus one poll.
+// tag = (Match epoch << 8) | (iteration + 1): never 0, unique across the iterations of consecutive Matches.
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned lo = (unsigned)b, hi = (unsigned)(b >> 32);
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+}
+__device__ __forceinline__ bool ll_load(const uint4* p, unsigned tag, double& v) {
+    unsigned lo, t0, hi, t1;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(p) : "memory");
+    v = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+    return t0 == tag && t1 == tag;
+}
+static constexpr int kLlPoseLen = 16;  // R[9], t[3], done, pad
+
+// Everything gn_step reads from the device state; a caller that has idle time before the totals are ready loads it early
+// (one L2 round trip off the critical path).
+struct GnPre {
+    double R[9], t[3], last_rot, last_pos, cand0, hits0;
+    int it;
+};
+__device__ __forceinline__ void gn_load(const GnState* s, GnPre& q) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) q.R[i] = __ldcg(&s->R[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) q.t[i] = __ldcg(&s->t[i]);
+    q.last_rot = __ldcg(&s->last_rot);
+    q.last_pos = __ldcg(&s->last_pos);
+    q.cand0 = __ldcg(&s->cand_total);
+    q.hits0 = __ldcg(&s->hits_total);
+    q.it = __ldcg(&s->iter);
+}
+
 // One Gauss-Newton step from the reduced totals `tot[kNumAcc]`: fills H/g, solves, updates the pose in `s`,
-// applies the plug-in's stop rule.  Executed by a single thread: every global read is issued up front (one L2
-// round trip instead of ~30 serialized ones), the arithmetic runs on locals, the results are stored at the end.
-__device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p, fls_iter_log* log, int log_cap, int* release_flag = nullptr,
-                               int release_value = 0) {
+// applies the plug-in's stop rule.  Executed by a single thread: the arithmetic runs on locals, what the other CTAs wait
+// for (pose + done) goes out first — as LL records when `ll_pose` is given, else as state stores + release flag — and
+// the bookkeeping follows.
+__device__ inline void gn_step_pre(GnState* s, const GnPre& q, const double* tot, const GnParams& p, fls_iter_log* log, int log_cap,
+                                   int* release_flag, int release_value, uint4* ll_pose, unsigned ll_tag) {
     double R[9], t[3];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = __ldcg(&s->R[i]);
+    for (int i = 0; i < 9; ++i) R[i] = q.R[i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) t[i] = __ldcg(&s->t[i]);
-    const double last_rot = __ldcg(&s->last_rot), last_pos = __ldcg(&s->last_pos);
-    const double cand0 = __ldcg(&s->cand_total), hits0 = __ldcg(&s->hits_total);
-    const int it = __ldcg(&s->iter);
+    for (int i = 0; i < 3; ++i) t[i] = q.t[i];
+    const double last_rot = q.last_rot, last_pos = q.last_pos;
+    const double cand0 = q.cand0, hits0 = q.hits0;
+    const int it = q.it;
 
     double H[36], g[6], dx[6] = {0, 0, 0, 0, 0, 0};
     for (int r = 0; r < 6; ++r)
@@ -80,12 +117,6 @@ __device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p,
     for (int a = 0; a < 6; ++a) g[a] = tot[21 + a];
     const long long n_valid = (long long)(tot[kAccValid] + 0.5);
     const double sum_res = tot[kAccRes];
-
-    // pose before the update (LOAM-iVox map insertion rule)
-#pragma unroll
-    for (int i = 0; i < 9; ++i) s->Rprev[i] = R[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) s->tprev[i] = t[i];
 
     bool stop = false;
     int converged = -1, failed = 0;
@@ -137,7 +168,14 @@ __device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p,
         }
         if (it + 1 >= p.max_iterations) stop = true;
     }
-    // ---- publish: what the other CTAs wait for goes out first (pose + done), then the hand-over flag, then the rest
+    // ---- publish: what the other CTAs wait for goes out first
+    if (ll_pose) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) ll_store(ll_pose + i, R[i], ll_tag);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ll_store(ll_pose + 9 + i, t[i], ll_tag);
+        ll_store(ll_pose + 12, stop ? 1.0 : 0.0, ll_tag);
+    }
 #pragma unroll
     for (int i = 0; i < 9; ++i) s->R[i] = R[i];
 #pragma unroll
@@ -147,6 +185,11 @@ __device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p,
         __threadfence();
         atomicExch(release_flag, release_value);
     }
+    // pose before the update (LOAM-iVox map insertion rule)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s->Rprev[i] = q.R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s->tprev[i] = q.t[i];
     s->last_rot = new_last_rot;
     s->last_pos = new_last_pos;
     for (int i = 0; i < 36; ++i) s->H[i] = H[i];
@@ -171,6 +214,13 @@ __device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p,
         L.sum_residual = sum_res;
         L.n_valid = n_valid;
     }
+}
+
+__device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p, fls_iter_log* log, int log_cap, int* release_flag = nullptr,
+                               int release_value = 0) {
+    GnPre q;
+    gn_load(s, q);
+    gn_step_pre(s, q, tot, p, log, log_cap, release_flag, release_value, nullptr, 0u);
 }
 
 // Tail of one iteration of a persistent GN loop (all threads of all CTAs call it with their per-thread sums):

@@ -30,8 +30,8 @@ struct Handle {
     DevBuf<unsigned char> flags;
     DevBuf<double> partials;
     DevBuf<int> sync_buf;  // work / arrive counters + release flag of the persistent LOAM kernel
-    DevBuf<unsigned long long> dbg_cta;  // FLS_DEBUG_TIMING only
-    int dbg_grid = 0;
+    DevBuf<uint4> ll_rows;      // LL hand-over records of the persistent LOAM-iVox kernel: [grid][32] rows + pose record
+    unsigned match_epoch = 0;   // tag prefix of those records
     DevBuf<GnState> state;
     GnState* h_state = nullptr;  // pinned
     DevBuf<fls_iter_log> log;

@@ -7,7 +7,7 @@
 
 namespace fls {
 
-static constexpr int kP2PlaneBlock = 384;  // 12 warps: consecutive chunks share L1, and the hand-over folds 3x fewer CTA rows
+static constexpr int kP2PlaneBlock = 768;  // default shape of the persistent LOAM-iVox kernel: one 24-warp CTA per SM (fls_p2plane.cu)
 static constexpr int kNdtBlock = 128;
 static constexpr int kIcpBlock = 128;
 static constexpr int kLoamBlock = 128;
@@ -22,21 +22,18 @@ struct P2PlaneLoopArgs {
     float4* __restrict__ rec0;  // persistent per-point record: J0..J3
     float4* __restrict__ rec1;  //                              J4, J5, |d|, 1
     unsigned char* __restrict__ flags;
-    double* __restrict__ partials;  // [chunks][kAccStride] — one row per 128-point chunk
-    int* sync;       // [2*max_iterations]: per iteration {next chunk to hand out, CTAs arrived}; zeroed per Match
-    int* sync_flag;  // iterations completed (release flag of the hand-over)
-    unsigned long long* dbg_cta;  // optional [grid][4] per-CTA timestamps of iteration 1 (FLS_DEBUG_TIMING), may be null
+    uint4* rows;        // [grid][32] LL records {lo, tag, hi, tag}: one per CTA and sum (fls_gn.cuh)
+    uint4* ll_pose;     // [kLlPoseLen] LL records: next pose + stop word, published by the folding CTA
+    unsigned tag_base;  // Match epoch << 8
     GnParams gp;
     fls_iter_log* log;
     int log_cap;
 };
 int p2plane_grid(int n, int device);
 int p2plane_chunks(int n);            // warp-sized (32-point) work chunks
-int p2plane_groups(int n);            // groups of 32 chunks
-size_t p2plane_partials_len(int n);   // doubles in the partial-sum buffer (chunk rows + group rows)
 void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st);
-void prepare_queries(const float4* d_src, int n, const double* T_colmajor, GnState* d_state, float inv_res, unsigned char* d_flags, int* d_sync,
-                     int n_sync, float4* d_sorted, BuildScratch& sc, cudaStream_t st, int* launches);
+void prepare_queries(const float4* d_src, int n, const double* T_colmajor, GnState* d_state, const IvoxView& map, unsigned char* d_flags,
+                     float4* d_sorted, BuildScratch& sc, cudaStream_t st, int* launches);
 // LOAM-iVox Match-internal AddCloudToLocalMap: classify + compact the points that enter the map (d_world, d_out: n records)
 size_t select_ivox_inserts(const IvoxView& map, const float4* d_src, int n, const double* R_prev, const double* t_prev, const double* R_fin,
                            const double* t_fin, double filter, float4* d_world, float4* d_out, BuildScratch& sc, cudaStream_t st, int* launches);

@@ -117,6 +117,8 @@ int extract_features_device(int device, const float* depth, const int* col, size
                             fls_match_stats* stats);
 
 // repack caller records (stride >= 20, intensity at byte 16) into packed float4 on the device
+int project_device(int device, const void* raw, const int* ring, size_t n, size_t stride, int V, int H, float h_res, float min_d, float max_d,
+                   float* ordered_out, float* depth_out, int* col_out, int* row_start, int* row_end, size_t* n_out);
 void launch_repack(const unsigned char* d_raw, size_t n, size_t stride, float4* d_out, cudaStream_t st);
 // TransformPointCloud(cloud, Mat4d) with R, t cast to float first (pointcloud_utility.h:141-158 upstream); T column-major
 void launch_transform_f(const float4* d_in, size_t n, const double* T_colmajor, float4* d_out, cudaStream_t st);

@@ -99,6 +99,10 @@ struct Top6q {
 #undef FLS_CEQ
 };
 
+__device__ __forceinline__ float dist2_fast(float px, float py, float pz, float qx, float qy, float qz) {
+    const float dx = px - qx, dy = py - qy, dz = pz - qz;
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
 __device__ __forceinline__ unsigned qkey(float d, float r2, unsigned jl) {
     return (d < r2) ? ((__float_as_uint(d) & 0xffffffc0u) | jl) : 0xffffffffu;  // d < max_range^2 (voxel_grid_node.cpp:27 upstream)
 }
@@ -114,6 +118,18 @@ __device__ __forceinline__ void knn5_stream(const IvoxView& m, float qx, float q
     n_cand = count;
     const float4* __restrict__ L = m.lists + start;
     const float r2 = m.max_range2;
+    // A run is ~4 cache lines and the scan below touches them one after the other; when a line is not on chip yet (first
+    // touch of a voxel in this Match) that would be one exposed HBM round trip per line.  Requesting the rest of the run
+    // up front overlaps them (lanes that share a run issue the same addresses: one request).
+    if (m.prefetch) {
+        const char* pl = reinterpret_cast<const char*>(L);
+        const unsigned bytes = count * 16u;
+        if (m.prefetch == 1) {
+            for (unsigned off = 128u; off < bytes; off += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + off));
+        } else {
+            for (unsigned off = 128u; off < bytes; off += 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + off));
+        }
+    }
     if (count > 64u) {  // position does not fit the 6-bit field
         knn5_exact(L, start, count, r2, qx, qy, qz, nn);
         return;
@@ -121,24 +137,45 @@ __device__ __forceinline__ void knn5_stream(const IvoxView& m, float qx, float q
     Top6q t;
     t.init();
     unsigned j = 0;
+    bool amb;
+    if (m.fast_knn) {
+        // every candidate of the stencil is provably inside max_range (host check, fls_api.cu), so the range test is
+        // dropped, and the distance may be contracted to FMAs: it then differs from the reference rounding by <= 2 ulp,
+        // which can only reorder keys whose 26-bit prefixes are equal or adjacent — those queries take the exact path
 #pragma unroll 1
-    for (; j + 4 <= count; j += 4) {
-        const float4 p0 = __ldg(L + j), p1 = __ldg(L + j + 1), p2 = __ldg(L + j + 2), p3 = __ldg(L + j + 3);
-        const float e0 = dist2_ref(p0.x, p0.y, p0.z, qx, qy, qz);
-        const float e1 = dist2_ref(p1.x, p1.y, p1.z, qx, qy, qz);
-        const float e2 = dist2_ref(p2.x, p2.y, p2.z, qx, qy, qz);
-        const float e3 = dist2_ref(p3.x, p3.y, p3.z, qx, qy, qz);
-        t.push(qkey(e0, r2, j));
-        t.push(qkey(e1, r2, j + 1));
-        t.push(qkey(e2, r2, j + 2));
-        t.push(qkey(e3, r2, j + 3));
-    }
+        for (; j + 4 <= count; j += 4) {
+            const float4 p0 = __ldg(L + j), p1 = __ldg(L + j + 1), p2 = __ldg(L + j + 2), p3 = __ldg(L + j + 3);
+            t.push((__float_as_uint(dist2_fast(p0.x, p0.y, p0.z, qx, qy, qz)) & 0xffffffc0u) | j);
+            t.push((__float_as_uint(dist2_fast(p1.x, p1.y, p1.z, qx, qy, qz)) & 0xffffffc0u) | (j + 1));
+            t.push((__float_as_uint(dist2_fast(p2.x, p2.y, p2.z, qx, qy, qz)) & 0xffffffc0u) | (j + 2));
+            t.push((__float_as_uint(dist2_fast(p3.x, p3.y, p3.z, qx, qy, qz)) & 0xffffffc0u) | (j + 3));
+        }
 #pragma unroll 1
-    for (; j < count; ++j) {
-        const float4 p = __ldg(L + j);
-        t.push(qkey(dist2_ref(p.x, p.y, p.z, qx, qy, qz), r2, j));
+        for (; j < count; ++j) {
+            const float4 p = __ldg(L + j);
+            t.push((__float_as_uint(dist2_fast(p.x, p.y, p.z, qx, qy, qz)) & 0xffffffc0u) | j);
+        }
+        amb = ((t.k1 >> 6) - (t.k0 >> 6) <= 1u && t.k1 != 0xffffffffu) || ((t.k5 >> 6) - (t.k4 >> 6) <= 1u && t.k5 != 0xffffffffu);
+    } else {
+#pragma unroll 1
+        for (; j + 4 <= count; j += 4) {
+            const float4 p0 = __ldg(L + j), p1 = __ldg(L + j + 1), p2 = __ldg(L + j + 2), p3 = __ldg(L + j + 3);
+            const float e0 = dist2_ref(p0.x, p0.y, p0.z, qx, qy, qz);
+            const float e1 = dist2_ref(p1.x, p1.y, p1.z, qx, qy, qz);
+            const float e2 = dist2_ref(p2.x, p2.y, p2.z, qx, qy, qz);
+            const float e3 = dist2_ref(p3.x, p3.y, p3.z, qx, qy, qz);
+            t.push(qkey(e0, r2, j));
+            t.push(qkey(e1, r2, j + 1));
+            t.push(qkey(e2, r2, j + 2));
+            t.push(qkey(e3, r2, j + 3));
+        }
+#pragma unroll 1
+        for (; j < count; ++j) {
+            const float4 p = __ldg(L + j);
+            t.push(qkey(dist2_ref(p.x, p.y, p.z, qx, qy, qz), r2, j));
+        }
+        amb = ((t.k0 >> 6) == (t.k1 >> 6) && t.k1 != 0xffffffffu) || ((t.k4 >> 6) == (t.k5 >> 6) && t.k5 != 0xffffffffu);
     }
-    const bool amb = ((t.k0 >> 6) == (t.k1 >> 6) && t.k1 != 0xffffffffu) || ((t.k4 >> 6) == (t.k5 >> 6) && t.k5 != 0xffffffffu);
     if (amb) {
         knn5_exact(L, start, count, r2, qx, qy, qz, nn);
         return;
@@ -159,7 +196,7 @@ __device__ __forceinline__ bool p2plane_point(const IvoxView& map, const float4 
     const float qz = xform_row_d(pose[6], pose[7], pose[8], pose[11], (double)sp.x, (double)sp.y, (double)sp.z);
     Top5 nn;
     knn5_stream(map, qx, qy, qz, nn, n_cand);
-    n_fallback = (unsigned)clock64();  // DEBUG: low 32 bits of the SM clock after the k-NN phase
+    n_fallback = 0;
     if (!nn.full()) return false;  // fewer than 5 neighbours (:271-273)
     const unsigned js[5] = {nn.idx(nn.k0), nn.idx(nn.k1), nn.idx(nn.k2), nn.idx(nn.k3), nn.idx(nn.k4)};
     return plane_term(map.lists, js, sp, qx, qy, qz, pose, plane_thres, J, ad, n_fallback);
@@ -172,16 +209,16 @@ template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs a) {
     constexpr int W = BLOCK / 32;
     __shared__ double s_pose[12];
-    __shared__ double s_rec[W][32][kRecW];
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    double (*s_rec)[32][kRecW] = reinterpret_cast<double (*)[32][kRecW]>(s_dyn);  // [W][32][kRecW] per-lane staging records
     __shared__ double s_red[W][32];
-    __shared__ int s_last;
+    __shared__ int s_done;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_chunks = (a.n + 31) >> 5;              // warp-sized chunks
-    const int n_groups = ((int)gridDim.x + 31) >> 5;   // groups of 32 CTAs
+    const int n_chunks = (a.n + 31) >> 5;  // warp-sized chunks
     const int n_warps = (int)gridDim.x * W;
-    double* __restrict__ rows = a.partials;                              // [gridDim.x][32]  one row per CTA
-    double* __restrict__ grows = a.partials + (size_t)gridDim.x * 32;    // [n_groups][32]
-    int* gcount = a.sync + 2 * a.gp.max_iterations + 1;                  // [n_groups], self-resetting
+    // CTA 0 folds and solves; chunks are dealt from the highest CTA index down so that CTA 0 is the one that stays idle
+    // whenever the grid has more warps than the scan has chunks (p2plane_grid adds one CTA for that purpose)
+    const int first_chunk = ((int)gridDim.x - 1 - (int)blockIdx.x) * W + warp;
 
     // which product of record columns lane k accumulates: sum_k = sgn * sum_p rec[p][ca] * rec[p][cb]
     int ca = kRecOne, cb = kRecOne;
@@ -205,24 +242,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
         sgn = 0.0;
     }
 
+    if (threadIdx.x < 9) s_pose[threadIdx.x] = __ldcg(&a.state->R[threadIdx.x]);
+    else if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(&a.state->t[threadIdx.x - 9]);
+    __syncthreads();
+
     for (int it = 0; it < a.gp.max_iterations; ++it) {
-        if (threadIdx.x < 9) s_pose[threadIdx.x] = __ldcg(&a.state->R[threadIdx.x]);
-        else if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(&a.state->t[threadIdx.x - 9]);
+        const unsigned tag = a.tag_base | (unsigned)(it + 1);
         if (blockIdx.x == 0 && threadIdx.x == 0 && it < 16) a.state->dbg[it][0] = globaltimer_ns();
-        __syncthreads();
-        if (a.dbg_cta && it == 1 && threadIdx.x == 0) a.dbg_cta[blockIdx.x * 4 + 0] = globaltimer_ns();
 
         double acc = 0.0;  // lane k's running sum over every chunk of this warp
         // warp-granular work loop, static round-robin over 32-point chunks: no barrier, no atomics inside
         // (consecutive chunks stay in one CTA: Morton neighbours share candidate lists in L1 — spreading them over SMs
         //  for balance was measured 35 % slower)
-        // (dealing runs of 4 chunks round-robin over CTAs was also tried: slowest CTA 14.6 -> 13.4 us but median
-        //  9.5 -> 10.3 us, no net gain)
-        for (int chunk = blockIdx.x * W + warp; chunk < n_chunks; chunk += n_warps) {
+        for (int chunk = first_chunk; chunk < n_chunks; chunk += n_warps) {
             const int i = (chunk << 5) + lane;
             double J[6] = {0, 0, 0, 0, 0, 0}, ad = 0.0, vflag = 0.0;
             unsigned n_cand = 0, n_fb = 0;
-            const unsigned dbg_t0 = (unsigned)clock64();
             if (i < a.n) {
                 const float4 sp = a.src[i];
                 bool use = p2plane_point(a.map, sp, s_pose, a.plane_thres, J, ad, n_cand, n_fb);
@@ -242,24 +277,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
                 }
                 vflag = use ? 1.0 : 0.0;
             }
-            const unsigned dbg_t1 = (unsigned)clock64();
-            if (a.dbg_cta && it == 1) {  // DEBUG: per-warp phase cycles (max over lanes of k-NN phase, list length)
-                unsigned knn_c = (i < a.n && n_fb) ? (n_fb - dbg_t0) : 0u;
-                unsigned mx = n_cand, sm = n_cand;
-                for (int o = 16; o > 0; o >>= 1) {
-                    knn_c = max(knn_c, __shfl_xor_sync(0xffffffffu, knn_c, o));
-                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    sm += __shfl_xor_sync(0xffffffffu, sm, o);
-                }
-                if (lane == 0) {
-                    unsigned long long* w = a.dbg_cta + (size_t)gridDim.x * 4 + (size_t)(blockIdx.x * W + warp) * 4;
-                    w[0] = dbg_t1 - dbg_t0;
-                    w[1] = knn_c;
-                    w[2] = mx;
-                    w[3] = sm;
-                }
-            }
-            n_fb = 0;
             double* rec = s_rec[warp][lane];
 #pragma unroll
             for (int k = 0; k < 6; ++k) rec[k] = J[k];
@@ -273,53 +290,64 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
             for (int p = 0; p < 32; ++p) acc += s_rec[warp][p][ca] * s_rec[warp][p][cb];
             __syncwarp();
         }
-        // ---- CTA row, then the last CTA of each group of 32 folds the group (fixed order at every level) ------------
-        if (a.dbg_cta && it == 1 && lane == 0) {
-            if (warp == 0) a.dbg_cta[blockIdx.x * 4 + 1] = globaltimer_ns();
-            if (warp == W - 1) a.dbg_cta[blockIdx.x * 4 + 2] = globaltimer_ns();
-        }
+        // ---- CTA row: one LL record per sum, no fence, no atomic ----------------------------------------------------------
         s_red[warp][lane] = acc * sgn;
         __syncthreads();
-        if (a.dbg_cta && it == 1 && threadIdx.x == 0) a.dbg_cta[blockIdx.x * 4 + 3] = globaltimer_ns();
         if (warp == 0) {
             double v = 0;
 #pragma unroll
             for (int w = 0; w < W; ++w) v += s_red[w][lane];
-            rows[(size_t)blockIdx.x * 32 + lane] = v;
-            // ---- iteration hand-over: ONE fence + ONE atomic per CTA; the CTA that arrives last folds every row
-            __threadfence();
-            int last = 0;
-            if (lane == 0) last = (atomicAdd(&a.sync[2 * it + 1], 1) == (int)gridDim.x - 1) ? 1 : 0;
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (lane == 0) s_last = last;
+            ll_store(a.rows + (size_t)blockIdx.x * 32 + lane, v, tag);
         }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            if (threadIdx.x == 0 && it < 16) a.state->dbg[it][1] = globaltimer_ns();
-            // fixed-order fold of the gridDim.x CTA rows: warp w takes rows w, w+W, ...; 4 independent partial sums per
-            // lane keep ~4 x 32 loads in flight; (a0+a1)+(a2+a3), then warps 0..W-1
-            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        if (blockIdx.x == 0) {
+            // ---- fold: warp w owns rows w, w+W, ...; every sweep re-reads all of them (independent loads, one L2 round
+            // trip) until each carries this iteration's tag, then the sums are taken in a fixed order — bitwise
+            // reproducible, and the fold is finished one sweep after the slowest CTA's row lands
+            GnPre pre;
+            if (threadIdx.x == 0) gn_load(a.state, pre);  // off the critical path: the state is stable until gn_step below
+            __syncthreads();  // s_red is free again
             const int nrows = (int)gridDim.x;
-            int r = warp;
-            for (; r + 7 * W < nrows; r += 8 * W) {  // 8 loads in flight per lane
-                const double v0 = __ldcg(&rows[(size_t)r * 32 + lane]), v1 = __ldcg(&rows[(size_t)(r + W) * 32 + lane]);
-                const double v2 = __ldcg(&rows[(size_t)(r + 2 * W) * 32 + lane]), v3 = __ldcg(&rows[(size_t)(r + 3 * W) * 32 + lane]);
-                const double v4 = __ldcg(&rows[(size_t)(r + 4 * W) * 32 + lane]), v5 = __ldcg(&rows[(size_t)(r + 5 * W) * 32 + lane]);
-                const double v6 = __ldcg(&rows[(size_t)(r + 6 * W) * 32 + lane]), v7 = __ldcg(&rows[(size_t)(r + 7 * W) * 32 + lane]);
-                a0 += v0; a1 += v1; a2 += v2; a3 += v3;
-                a0 += v4; a1 += v5; a2 += v6; a3 += v7;
+            double sum;
+            for (;;) {
+                bool ok = true;
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                int r = warp;
+                for (; r + 7 * W < nrows; r += 8 * W) {  // 8 independent 16-byte loads in flight per lane
+                    double v0, v1, v2, v3, v4, v5, v6, v7;
+                    const bool k0 = ll_load(a.rows + (size_t)r * 32 + lane, tag, v0);
+                    const bool k1 = ll_load(a.rows + (size_t)(r + W) * 32 + lane, tag, v1);
+                    const bool k2 = ll_load(a.rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
+                    const bool k3 = ll_load(a.rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
+                    const bool k4 = ll_load(a.rows + (size_t)(r + 4 * W) * 32 + lane, tag, v4);
+                    const bool k5 = ll_load(a.rows + (size_t)(r + 5 * W) * 32 + lane, tag, v5);
+                    const bool k6 = ll_load(a.rows + (size_t)(r + 6 * W) * 32 + lane, tag, v6);
+                    const bool k7 = ll_load(a.rows + (size_t)(r + 7 * W) * 32 + lane, tag, v7);
+                    ok = ok && k0 && k1 && k2 && k3 && k4 && k5 && k6 && k7;
+                    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+                    a0 += v4; a1 += v5; a2 += v6; a3 += v7;
+                }
+                for (; r + 3 * W < nrows; r += 4 * W) {
+                    double v0, v1, v2, v3;
+                    const bool k0 = ll_load(a.rows + (size_t)r * 32 + lane, tag, v0);
+                    const bool k1 = ll_load(a.rows + (size_t)(r + W) * 32 + lane, tag, v1);
+                    const bool k2 = ll_load(a.rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
+                    const bool k3 = ll_load(a.rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
+                    ok = ok && k0 && k1 && k2 && k3;
+                    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+                }
+                for (; r < nrows; r += W) {
+                    double v0;
+                    ok = ok && ll_load(a.rows + (size_t)r * 32 + lane, tag, v0);
+                    a0 += v0;
+                }
+                sum = (a0 + a1) + (a2 + a3);
+                if (__all_sync(0xffffffffu, ok)) break;
+                __nanosleep(100);
             }
-            for (; r + 3 * W < nrows; r += 4 * W) {
-                a0 += __ldcg(&rows[(size_t)r * 32 + lane]);
-                a1 += __ldcg(&rows[(size_t)(r + W) * 32 + lane]);
-                a2 += __ldcg(&rows[(size_t)(r + 2 * W) * 32 + lane]);
-                a3 += __ldcg(&rows[(size_t)(r + 3 * W) * 32 + lane]);
-            }
-            for (; r < nrows; r += W) a0 += __ldcg(&rows[(size_t)r * 32 + lane]);
-            s_red[warp][lane] = (a0 + a1) + (a2 + a3);
+            s_red[warp][lane] = sum;
             __syncthreads();
             if (warp == 0) {
+                if (lane == 0 && it < 16) a.state->dbg[it][1] = globaltimer_ns();
                 double t = 0;
 #pragma unroll
                 for (int w = 0; w < W; ++w) t += s_red[w][lane];
@@ -328,18 +356,20 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
                 __syncwarp();
                 if (lane == 0) {
                     if (it < 16) a.state->dbg[it][2] = globaltimer_ns();
-                    gn_step(a.state, s_red[0], a.gp, a.log, a.log_cap, a.sync_flag, it + 1);  // releases as soon as the pose is out
+                    gn_step_pre(a.state, pre, s_red[0], a.gp, a.log, a.log_cap, nullptr, 0, a.ll_pose, tag);
                     if (it < 16) a.state->dbg[it][3] = globaltimer_ns();
                 }
             }
-        } else if (threadIdx.x == 0) {
-            // acquire: plain L2 loads with back-off — hundreds of CTAs poll this word while the stragglers still work,
-            // and atomics on one hot line would serialise in a single L2 slice and slow the whole memory system
-            while (*reinterpret_cast<volatile int*>(a.sync_flag) < it + 1) __nanosleep(200);
-            __threadfence();
+        }
+        // ---- next pose: everybody polls the LL pose record (12 values + the stop word) -----------------------------------
+        if (threadIdx.x < 13) {
+            double v;
+            while (!ll_load(a.ll_pose + threadIdx.x, tag, v)) __nanosleep(100);
+            if (threadIdx.x < 12) s_pose[threadIdx.x] = v;
+            else s_done = v != 0.0;
         }
         __syncthreads();
-        if (__ldcg(&a.state->done)) break;
+        if (s_done) break;
     }
 }
 
@@ -364,11 +394,10 @@ struct PoseArg {
 // `hbits` more bits each of x and y; wrap-around beyond that only costs locality, never correctness.
 // key_bits = 12 + 2*hbits: 24 bits = three 8-bit radix passes, 16 bits = two.
 __global__ void p2plane_prep_kernel(const float4* __restrict__ src, int n, PoseArg pose, float inv_res, int hbits, unsigned* __restrict__ keys,
-                                    unsigned* __restrict__ idx, unsigned char* __restrict__ flags, int* __restrict__ sync, int n_sync,
-                                    GnState* __restrict__ s) {
+                                    unsigned* __restrict__ idx, unsigned char* __restrict__ flags, GnState* __restrict__ s,
+                                    const HashSlot* __restrict__ ctab, unsigned cmask, const float4* __restrict__ lists) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0) {
-        for (int k = threadIdx.x; k < n_sync; k += blockDim.x) sync[k] = 0;
         if (threadIdx.x == 0) {
             for (int k = 0; k < 9; ++k) s->R[k] = s->R0[k] = s->Rprev[k] = pose.R[k];
             for (int k = 0; k < 3; ++k) s->t[k] = s->t0[k] = s->tprev[k] = pose.t[k];
@@ -397,6 +426,22 @@ __global__ void p2plane_prep_kernel(const float4* __restrict__ src, int n, PoseA
     for (int b = 0; b < hbits; ++b) hi |= (((hx >> b) & 1u) << (2 * b)) | (((hy >> b) & 1u) << (2 * b + 1));
     keys[i] = lo | (hi << 12);
     idx[i] = (unsigned)i;
+    // Warm L2 for the first iteration: the candidate run of the voxel this point starts in is requested now and arrives
+    // while the radix sort runs (the GN kernel is latency-bound on exactly these lines when they come from HBM).  One
+    // lane per distinct voxel of the warp issues the prefetches.
+    if (ctab) {
+        const unsigned long long key = pack_key((int)kx, (int)ky, (int)kz);
+        const unsigned peers = __match_any_sync(__activemask(), key);
+        if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) {
+            unsigned start, count;
+            if (table_find(ctab, cmask, key, start, count)) {
+                const char* p = reinterpret_cast<const char*>(lists + start);
+                const unsigned bytes = count * 16u;
+                for (unsigned off = 0; off < bytes; off += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + bytes - 1));
+            }
+        }
+    }
 }
 
 __global__ void gather4_kernel(const float4* __restrict__ src, const unsigned* __restrict__ idx, int n, float4* __restrict__ dst) {
@@ -489,47 +534,67 @@ __global__ void ivox_insert_scatter_kernel(const unsigned char* __restrict__ cls
     else if (c == 2) out[n1 + (unsigned)(excl[i] >> 32)] = world[i];
 }
 
-constexpr int kMinBlocks = 2;  // 2 x 384 threads: <= 80 registers, 24 warps / SM — enough resident warps to cover a 100k-point scan in one pass
+// Two shapes of the same kernel: 2 x 384 threads per SM (<= 80 registers) or 1 x 768 — the same 24 resident warps, half
+// the CTA rows to fold.  FLS_P2PLANE_BLOCK=384|768 overrides the default.
+template <int BLOCK>
+struct P2PlaneShape {
+    static constexpr int kMinB = BLOCK == 384 ? 2 : 1;
+    static const void* fn() { return (const void*)p2plane_gn_kernel<BLOCK, kMinB>; }
+    static size_t smem() { return (size_t)(BLOCK / 32) * 32 * kRecW * sizeof(double); }
+};
 
 }  // namespace
+
+int p2plane_block() {
+    static int block = 0;
+    if (!block) {
+        const char* e = std::getenv("FLS_P2PLANE_BLOCK");
+        block = (e && std::atoi(e) == 384) ? 384 : ((e && std::atoi(e) == 768) ? 768 : kP2PlaneBlock);
+    }
+    return block;
+}
 
 int p2plane_max_grid(int device) {
     static int cached[64] = {0};
     if (device >= 0 && device < 64 && cached[device]) return cached[device];
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2plane_gn_kernel<kP2PlaneBlock, kMinBlocks>, kP2PlaneBlock, 0);
+    if (p2plane_block() == 384) {
+        cudaFuncSetAttribute(P2PlaneShape<384>::fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2PlaneShape<384>::smem());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2plane_gn_kernel<384, 2>, 384, P2PlaneShape<384>::smem());
+    } else {
+        cudaFuncSetAttribute(P2PlaneShape<768>::fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2PlaneShape<768>::smem());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2plane_gn_kernel<768, 1>, 768, P2PlaneShape<768>::smem());
+    }
     const int g = sms * (per_sm > 0 ? per_sm : 1);
     if (device >= 0 && device < 64) cached[device] = g;
     return g;
 }
 
 int p2plane_chunks(int n) { return (n + 31) / 32; }
-// doubles needed by the partial-sum buffer: one 32-wide row per chunk + one per group of 32 chunks
-size_t p2plane_partials_len(int n) {
-    const size_t c = (size_t)p2plane_chunks(n);
-    return (c + (c + 31) / 32 + 2) * 32;
-}
-int p2plane_groups(int n) { return (p2plane_chunks(n) + 31) / 32; }
 
 int p2plane_grid(int n, int device) {
-    const int need = (p2plane_chunks(n) + (kP2PlaneBlock / 32) - 1) / (kP2PlaneBlock / 32);
+    const int W = p2plane_block() / 32;
+    const int need = (p2plane_chunks(n) + W - 1) / W;
     const int cap = p2plane_max_grid(device);
-    const int g = need < cap ? need : cap;
+    const int g = need + 1 < cap ? need + 1 : cap;  // + the folding CTA (stays without chunks when there is room)
     return g > 0 ? g : 1;
 }
 
 void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st) {
     P2PlaneLoopArgs args = a;
     void* params[] = {&args};
-    FLS_CUDA(cudaLaunchCooperativeKernel((const void*)p2plane_gn_kernel<kP2PlaneBlock, kMinBlocks>, dim3(grid), dim3(kP2PlaneBlock), params, 0,
-                                         st));
+    if (p2plane_block() == 384)
+        FLS_CUDA(cudaLaunchCooperativeKernel(P2PlaneShape<384>::fn(), dim3(grid), dim3(384), params, P2PlaneShape<384>::smem(), st));
+    else
+        FLS_CUDA(cudaLaunchCooperativeKernel(P2PlaneShape<768>::fn(), dim3(grid), dim3(768), params, P2PlaneShape<768>::smem(), st));
 }
 
 // Per-Match preparation: state init + counter / flag reset + locality keys (one kernel), then order the scan by the
 // voxel each point falls into at the initial pose (CUB radix sort of {key, index}, gather).
-void prepare_queries(const float4* d_src, int n, const double* T_colmajor, GnState* d_state, float inv_res, unsigned char* d_flags, int* d_sync,
-                     int n_sync, float4* d_sorted, BuildScratch& sc, cudaStream_t st, int* launches) {
+void prepare_queries(const float4* d_src, int n, const double* T_colmajor, GnState* d_state, const IvoxView& map, unsigned char* d_flags,
+                     float4* d_sorted, BuildScratch& sc, cudaStream_t st, int* launches) {
+    const float inv_res = map.inv_res;
     const int m = n > 0 ? n : 1;
     sc.k32a.reserve(m);
     sc.k32b.reserve(m);
@@ -546,8 +611,8 @@ void prepare_queries(const float4* d_src, int n, const double* T_colmajor, GnSta
     // Morton window is all the locality the L1 broadcast needs
     int key_bits = kb ? std::atoi(kb) : 16;
     if (key_bits != 16 && key_bits != 20 && key_bits != 24) key_bits = 16;
-    p2plane_prep_kernel<<<(m + 255) / 256, 256, 0, st>>>(d_src, n, pose, inv_res, (key_bits - 12) / 2, sc.k32a.p, sc.idx.p, d_flags, d_sync, n_sync,
-                                                        d_state);
+    p2plane_prep_kernel<<<(m + 255) / 256, 256, 0, st>>>(d_src, n, pose, inv_res, (key_bits - 12) / 2, sc.k32a.p, sc.idx.p, d_flags, d_state,
+                                                        std::getenv("FLS_NO_PREFETCH") ? nullptr : map.ctab, map.cmask, map.lists);
     if (launches) *launches += 1;
     if (n <= 0) return;
     size_t t1 = 0;

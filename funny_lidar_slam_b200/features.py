@@ -46,3 +46,43 @@ class FeatureExtractor:
                                       cluster.row_end_index_vec)
         cluster.corner_cloud = np.ascontiguousarray(cluster.ordered_cloud[ci])
         cluster.planar_cloud = np.ascontiguousarray(cluster.ordered_cloud[pi])
+
+
+class PointcloudProjector:
+    """Host-side mirror of loam::PointcloudProjector (include/loam/pointcloud_projector.h upstream): `Project(cluster)`
+    reads cluster.extra["raw_cloud"] ((n,4) xyzi or (n,8) pcl records, firing order) and cluster.extra["ring"] and
+    fills ordered_cloud / point_depth_vec / point_col_index_vec / row_start_index_vec / row_end_index_vec.
+    The IMU de-skew step of upstream is not applied (see fls_project in include/fls_b200.h)."""
+
+    def __init__(self, lidar_horizontal_scan: int, lidar_vertical_scan: int, lidar_horizontal_resolution: float, min_distance: float,
+                 max_distance: float, device: int = 0):
+        self.H, self.V = int(lidar_horizontal_scan), int(lidar_vertical_scan)
+        self.h_res, self.min_d, self.max_d = float(lidar_horizontal_resolution), float(min_distance), float(max_distance)
+        self.device = int(device)
+
+    def project_arrays(self, raw, ring):
+        raw = np.ascontiguousarray(raw, np.float32)
+        if raw.ndim != 2 or raw.shape[1] not in (4, 8):
+            raise ValueError("raw cloud must be (n,4) packed xyzi or (n,8) pcl records")
+        ring = np.ascontiguousarray(ring, np.int32)
+        cells = self.V * self.H
+        ordered = np.zeros((cells, 4), np.float32)
+        depth = np.zeros(cells, np.float32)
+        col = np.zeros(cells, np.int32)
+        rs = np.zeros(self.V, np.int32)
+        re = np.zeros(self.V, np.int32)
+        n_out = C.c_size_t(0)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = lib().fls_project(self.device, vp(raw), vp(ring), C.c_size_t(len(raw)), C.c_size_t(raw.shape[1] * 4), self.V, self.H,
+                               C.c_float(self.h_res), C.c_float(self.min_d), C.c_float(self.max_d), vp(ordered), vp(depth), vp(col), vp(rs),
+                               vp(re), C.byref(n_out))
+        check(rc, "fls_project")
+        return dict(ordered=ordered[:n_out.value].copy(), depth=depth, col=col, row_start=rs, row_end=re, n=n_out.value)
+
+    def Project(self, cluster: PointcloudCluster) -> None:
+        out = self.project_arrays(cluster.extra["raw_cloud"], cluster.extra["ring"])
+        cluster.ordered_cloud = out["ordered"]
+        cluster.point_depth_vec = out["depth"]
+        cluster.point_col_index_vec = out["col"]
+        cluster.row_start_index_vec = out["row_start"]
+        cluster.row_end_index_vec = out["row_end"]

@@ -14,6 +14,7 @@
  *   fls_fitness                <- RegistrationInterface::GetFitnessScore (registration_interface.h:19)
  *   fls_extract_features       <- loam::FeatureExtractor::ExtractFeatures
  *                                 (include/loam/feature_extractor.h:22, src/loam/feature_extractor.cpp:35-44)
+ *   fls_project                <- loam::PointcloudProjector::Project (src/loam/pointcloud_projector.cpp:32-133)
  *   fls_voxel_grid             <- VoxelGridCloud (include/common/pointcloud_utility.h:216-224,263-271)
  *
  * Conventions
@@ -194,6 +195,14 @@ typedef struct {
 int fls_extract_features(const fls_feature_cfg* cfg, const float* depth, const int32_t* col, size_t n, const int32_t* row_start,
                          const int32_t* row_end, int32_t n_rows, int32_t* corner_idx, size_t* n_corner, int32_t* planar_idx, size_t* n_planar,
                          fls_match_stats* stats);
+
+/* PointcloudProjector::Project (src/loam/pointcloud_projector.cpp:32-133): raw cloud + ring per point (firing order) ->
+ * ordered_cloud_ (packed float4, capacity n_rows*n_cols), point_depth_vec_ / point_col_index_vec_ (n_rows*n_cols entries, the
+ * first *n_ordered meaningful), row_start_index_vec_ / row_end_index_vec_ (n_rows).  The IMU de-skew of :100-103 is not
+ * applied (identity) — it depends on the pose buffer of the caller. */
+int fls_project(int device, const void* raw, const int32_t* ring, size_t n, size_t stride_bytes, int32_t n_rows, int32_t n_cols,
+                float horizontal_resolution, float min_distance, float max_distance, float* ordered, float* depth, int32_t* col,
+                int32_t* row_start, int32_t* row_end, size_t* n_ordered);
 
 const char* fls_strerror(int status);
 const char* fls_last_error(void); /* thread-local text of the last CUDA failure */

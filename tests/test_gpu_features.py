@@ -103,3 +103,62 @@ def test_corner_limit_and_dense_corners():
     assert len(gc) > 250  # the two long rings saturate at 6 x 20
     _check(_ring_case(rows, col_step=3), 0.05, 0.001)     # column gaps of 3: reach stays 5 (|dcol| <= 10 per step)
     _check(_ring_case(rows, col_step=11), 0.05, 0.001)    # gaps > 10: no suppression reach at all
+
+
+def _raw_scan(world, pose, sensor, seed, shuffle_cols=True):
+    """Raw cloud in a firing-like order (column-major over rings) with duplicate hits per cell, as a driver delivers it."""
+    sc = synth.make_scan(world, pose, sensor, seed=seed)
+    order = np.lexsort((sc["ring"], sc["col"]))
+    pts, ring = sc["points"][order], sc["ring"][order].astype(np.int32)
+    # a second, slightly different return for every 7th point: the later duplicate must lose its cell
+    dup = pts[::7].copy()
+    dup[:, :3] *= 1.0005
+    return np.concatenate([pts, dup]), np.concatenate([ring, ring[::7]])
+
+
+@pytest.mark.parametrize("sensor", ["vlp16", "hdl64"])
+def test_projector_matches_oracle_bit_for_bit(world, traj, sensor):
+    from funny_lidar_slam_b200.features import PointcloudProjector
+    from oracle import pyoracle as orc
+    sn = synth.SENSORS[sensor]
+    raw, ring = _raw_scan(world, traj[3], sensor, 31)
+    H, V = sn.cols, sn.lines
+    h_res = float(np.float32(2 * np.pi / H))
+    o = orc.project(raw, ring, V, H, h_res, 2.0, 80.0)
+    g = PointcloudProjector(H, V, h_res, 2.0, 80.0).project_arrays(raw, ring)
+    assert g["n"] == o["n"] and g["n"] > 1000
+    n = g["n"]
+    assert np.array_equal(g["ordered"], o["ordered"])
+    assert np.array_equal(g["depth"][:n], o["depth"][:n]) and np.array_equal(g["col"][:n], o["col"][:n])
+    assert np.array_equal(g["row_start"], o["row_start"]) and np.array_equal(g["row_end"], o["row_end"])
+    # and through the pcl::PointXYZI layout, feeding the extractor (projector -> features, both on the device)
+    from funny_lidar_slam_b200.features import FeatureExtractor
+    from funny_lidar_slam_b200.registration import PointcloudCluster
+    from tests.conftest import to_pcl
+    cl = PointcloudCluster(extra=dict(raw_cloud=to_pcl(raw), ring=ring))
+    PointcloudProjector(H, V, h_res, 2.0, 80.0).Project(cl)
+    assert np.array_equal(cl.ordered_cloud, o["ordered"])
+    fx = FeatureExtractor(1.0, 0.1)
+    fx.ExtractFeatures(cl)
+    oc, op, _ = orc.extract_features(o["depth"], o["col"], n, o["row_start"], o["row_end"], 1.0, 0.1)
+    assert np.array_equal(fx.corner_idx, oc) and np.array_equal(fx.planar_idx, op)
+
+
+def test_projector_edge_cases():
+    from funny_lidar_slam_b200.features import PointcloudProjector
+    from oracle import pyoracle as orc
+    rng = np.random.default_rng(3)
+    V, H = 4, 90
+    h_res = float(np.float32(2 * np.pi / H))
+    raw = np.zeros((400, 4), np.float32)
+    raw[:, :3] = rng.normal(0, 12, (400, 3))
+    raw[:5, :3] = 0.0            # zero range: gated out
+    raw[5:10, :3] *= 100.0       # beyond max range
+    ring = rng.integers(-1, V + 1, 400).astype(np.int32)  # includes invalid rings -1 and V
+    o = orc.project(raw, ring, V, H, h_res, 1.0, 60.0)
+    g = PointcloudProjector(H, V, h_res, 1.0, 60.0).project_arrays(raw, ring)
+    assert g["n"] == o["n"]
+    assert np.array_equal(g["ordered"], o["ordered"]) and np.array_equal(g["col"][:g["n"]], o["col"][:o["n"]])
+    assert np.array_equal(g["row_start"], o["row_start"]) and np.array_equal(g["row_end"], o["row_end"])
+    e = PointcloudProjector(H, V, h_res, 1.0, 60.0).project_arrays(np.zeros((0, 4), np.float32), np.zeros(0, np.int32))
+    assert e["n"] == 0 and list(e["row_start"]) == [5] * V and list(e["row_end"]) == [-6] * V
