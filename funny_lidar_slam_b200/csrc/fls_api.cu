@@ -23,8 +23,8 @@ Handle::Handle(const fls_config& c) : cfg(c) {
     FLS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     FLS_CUDA(cudaEventCreate(&ev0));
     FLS_CUDA(cudaEventCreate(&ev1));
-    FLS_CUDA(cudaMallocHost(&h_state, sizeof(GnState)));
-    state.reserve(1);
+    FLS_CUDA(cudaMallocHost(&h_state, sizeof(GnState) * kMaxBatch));
+    state.reserve(kMaxBatch);
     fit_out.reserve(2);
     ivox.set_resolution(cfg.ivox_resolution);
     ivox.key_mode = 0;
@@ -56,7 +56,7 @@ Handle::Handle(const fls_config& c) : cfg(c) {
     }
     if (cfg.flags & FLS_FLAG_ITER_LOG) {
         log_cap = cfg.max_iterations > 0 ? cfg.max_iterations : 1;
-        log.reserve(log_cap);
+        log.reserve((size_t)log_cap * kMaxBatch);
         h_log.resize(log_cap);
     }
 }
@@ -65,6 +65,7 @@ Handle::~Handle() {
     cudaSetDevice(cfg.device);
     if (stream) cudaStreamSynchronize(stream);
     if (h_state) cudaFreeHost(h_state);
+    if (h_batch) cudaFreeHost(h_batch);
     for (auto& e : prof_ev) cudaEventDestroy(e);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -173,47 +174,102 @@ int Handle::add_cloud_ivox(const void* pts, size_t n, size_t stride) {
     return rc;
 }
 
-int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st) {
+// The whole LoamPointToPlaneIVOX Match of `n_scans` independent scans in one persistent launch (K1, fls_p2plane.cu).
+// A single Match is the batch of one.
+int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* n, double* T, int* converged, fls_match_stats* st) {
     if (ivox.n_pts == 0) return FLS_ERR_NO_MAP;
-    const int ni = (int)n;
-    const int grid = p2plane_grid(ni, cfg.device);
-    rec0.reserve(n + 1);
-    rec1.reserve(n + 1);
-    flags.reserve(n + 1);
-    src_f.reserve(n + 1);
-    // hand-over buffers: one LL row per CTA + the LL pose record; tags are unique per (Match, iteration), so neither is
-    // ever cleared — only zeroed when (re)allocated, so that uninitialised memory cannot alias a tag
+    if (B < 1 || B > kMaxBatch) return FLS_ERR_INVALID_ARG;
+    int off[kMaxBatch + 1], grid_of[kMaxBatch], cta_begin[kMaxBatch + 1];
+    off[0] = 0;
+    cta_begin[0] = 0;
+    for (int s = 0; s < B; ++s) {
+        if (n[s] > 0x3fffffffull || (long long)off[s] + (long long)n[s] > 0x7ffffff0ll) return FLS_ERR_INVALID_ARG;
+        off[s + 1] = off[s] + (int)n[s];
+        grid_of[s] = p2plane_grid((int)n[s], cfg.device, B);
+        cta_begin[s + 1] = cta_begin[s] + grid_of[s];
+    }
+    const int n_total = off[B], grid = cta_begin[B];
+    const size_t nt = (size_t)n_total;
+    rec0.reserve(nt + 1);
+    rec1.reserve(nt + 1);
+    flags.reserve(nt + 1);
+    src_f.reserve(nt + 1);
+    state.reserve(kMaxBatch);
+    if (log_cap) log.reserve((size_t)log_cap * kMaxBatch);
+    // hand-over buffers: one LL row per CTA + one LL pose record per scan; tags are unique per (batch, iteration), so neither
+    // is ever cleared — only zeroed when (re)allocated, so that uninitialised memory cannot alias a tag
     {
         const size_t cap0 = ll_rows.cap;
-        ll_rows.reserve((size_t)grid * 32 + kLlPoseLen);
+        ll_rows.reserve((size_t)grid * 32 + (size_t)B * kLlPoseLen);
         if (ll_rows.cap != cap0) FLS_CUDA(cudaMemsetAsync(ll_rows.p, 0, ll_rows.cap * sizeof(uint4), stream));
     }
     match_epoch = (match_epoch + 1) & 0xffffffu;
     if (match_epoch == 0) match_epoch = 1;
-    // one prep kernel (state init, flag reset, locality keys) + radix sort + gather: the queries end up in Morton order of
-    // the voxel they fall into at the initial pose (locality only: the sums are order-free up to fp64 rounding, and the
-    // persistent per-point records live in the same order for the whole Match)
-    prepare_queries(d_src, ni, T, state.p, ivox_view(), flags.p, src_f.p, scratch, stream, &launches);
+    // ---- per-batch tables, staged in one pinned block and sent with one copy -------------------------------------------
+    const size_t o_pose = 0, o_off = o_pose + sizeof(PoseArg) * kMaxBatch, o_desc = o_off + sizeof(int) * (kMaxBatch + 4),
+                 o_ptr = o_desc + sizeof(P2PlaneScan) * kMaxBatch, o_cta = o_ptr + sizeof(void*) * kMaxBatch;
+    const size_t tbl_bytes = o_cta + sizeof(int) * (size_t)(grid + 4);
+    if (tbl_bytes > h_batch_cap) {
+        if (h_batch) cudaFreeHost(h_batch);
+        h_batch = nullptr;
+        h_batch_cap = 0;
+        FLS_CUDA(cudaMallocHost(&h_batch, tbl_bytes * 2));
+        h_batch_cap = tbl_bytes * 2;
+    }
+    d_batch.reserve(tbl_bytes);
+    PoseArg* hp = reinterpret_cast<PoseArg*>(h_batch + o_pose);
+    int* ho = reinterpret_cast<int*>(h_batch + o_off);
+    P2PlaneScan* hd = reinterpret_cast<P2PlaneScan*>(h_batch + o_desc);
+    const float4** hq = reinterpret_cast<const float4**>(h_batch + o_ptr);
+    int* hc = reinterpret_cast<int*>(h_batch + o_cta);
+    uint4* pose_base = ll_rows.p + (size_t)grid * 32;
+    for (int s = 0; s < B; ++s) {
+        const double* Ts = T + 16 * s;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) hp[s].R[r * 3 + c] = Ts[c * 4 + r];
+            hp[s].t[r] = Ts[12 + r];
+        }
+        ho[s] = off[s];
+        hq[s] = d_scans[s];
+        P2PlaneScan& d = hd[s];
+        d.src = src_f.p + off[s];
+        d.n = (int)n[s];
+        d.cta_begin = cta_begin[s];
+        d.cta_count = grid_of[s];
+        d.tag_base = match_epoch << 8;
+        d.state = state.p + s;
+        d.rec0 = rec0.p + off[s];
+        d.rec1 = rec1.p + off[s];
+        d.flags = flags.p + off[s];
+        d.rows = ll_rows.p + (size_t)cta_begin[s] * 32;
+        d.ll_pose = pose_base + (size_t)s * kLlPoseLen;
+        d.log = log_cap ? log.p + (size_t)s * log_cap : nullptr;
+        for (int k = 0; k < grid_of[s]; ++k) hc[cta_begin[s] + k] = s;
+    }
+    ho[B] = off[B];
+    FLS_CUDA(cudaMemcpyAsync(d_batch.p, h_batch, tbl_bytes, cudaMemcpyHostToDevice, stream));
+    h2d_bytes += (long long)tbl_bytes;
+    const PoseArg* d_poses = reinterpret_cast<const PoseArg*>(d_batch.p + o_pose);
+    const int* d_off = reinterpret_cast<const int*>(d_batch.p + o_off);
+    const P2PlaneScan* d_desc = reinterpret_cast<const P2PlaneScan*>(d_batch.p + o_desc);
+    const float4* const* d_ptrs = reinterpret_cast<const float4* const*>(d_batch.p + o_ptr);
+    const int* d_cta = reinterpret_cast<const int*>(d_batch.p + o_cta);
+    // one prep kernel (state init, flag reset, locality keys) + ONE radix sort + gather for the whole batch: the queries of
+    // every scan end up in Morton order of the voxel they fall into at the initial pose (locality only: the sums are
+    // order-free up to fp64 rounding, and the persistent per-point records live in the same order for the whole Match)
+    prepare_queries(d_ptrs, n_total, d_off, B, d_poses, state.p, ivox_view(), flags.p, src_f.p, scratch, stream, &launches);
     P2PlaneLoopArgs a;
-    a.src = src_f.p;
-    a.n = ni;
     a.map = ivox_view();
     a.plane_thres = cfg.point_to_planar_thres;
-    a.state = state.p;
-    a.rec0 = rec0.p;
-    a.rec1 = rec1.p;
-    a.flags = flags.p;
-    a.rows = ll_rows.p;
-    a.ll_pose = ll_rows.p + (size_t)grid * 32;
-    a.tag_base = match_epoch << 8;
     a.gp.method = FLS_P2PLANE_IVOX;
     a.gp.max_iterations = cfg.max_iterations;
     a.gp.min_effective = 50;
     a.gp.n_blocks = grid;
     a.gp.rot_thres = cfg.rotation_converge_thres;
     a.gp.pos_thres = cfg.position_converge_thres;
-    a.log = log.p;
     a.log_cap = log_cap;
+    a.scans = d_desc;
+    a.cta_scan = d_cta;
     // roofline accounting (SURVEY.md §8d, K1 — the REFERENCE algorithm's traffic): 16 B source point + n_stencil x 16 B
     // slot probes + 32 B persistent record per point-iteration, 16 B per map record resident in the stencil voxels.
     per_point_iter_bytes = 16 + 16LL * a.map.n_stencil + 32;
@@ -224,10 +280,69 @@ int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* co
     if (profile) FLS_CUDA(cudaEventRecord(prof_ev[1], stream));
     launches++;
     fused_loop = true;
-    last_src = d_src;
-    last_src_n = n;
-    const int rc = finish_match(T, converged, st, (long long)n);
+    last_src = d_scans[0];
+    last_src_n = n[0];
+    // ---- read back: every scan's state (+ iteration log of scan 0) -----------------------------------------------------
+    FLS_CUDA(cudaMemcpyAsync(h_state, state.p, sizeof(GnState) * (size_t)B, cudaMemcpyDeviceToHost, stream));
+    d2h_bytes += (long long)(sizeof(GnState) * (size_t)B);
+    if (log_cap) {
+        FLS_CUDA(cudaMemcpyAsync(h_log.data(), log.p, sizeof(fls_iter_log) * log_cap, cudaMemcpyDeviceToHost, stream));
+        d2h_bytes += (long long)(sizeof(fls_iter_log) * log_cap);
+    }
+    end_call(st);
+    float kernel_ms = 0.f;
+    if (profile) FLS_CUDA(cudaEventElapsedTime(&kernel_ms, prof_ev[0], prof_ev[1]));
+    batch_n.assign(n, n + B);
+    for (int s = 0; s < B; ++s) {
+        const GnState& gs = h_state[s];
+        double* Ts = T + 16 * s;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) Ts[c * 4 + r] = gs.R[r * 3 + c];
+            Ts[12 + r] = gs.t[r];
+        }
+        Ts[3] = Ts[7] = Ts[11] = 0.0;
+        Ts[15] = 1.0;
+        if (converged) converged[s] = gs.converged;
+        if (st) {
+            fls_match_stats& o = st[s];
+            if (s > 0) std::memset(&o, 0, sizeof(o));  // call-level figures (times, launches, copies) are reported on scan 0
+            o.iterations = gs.iter;
+            o.converged = gs.converged;
+            o.n_source = (long long)n[s];
+            o.n_valid = gs.n_valid;
+            o.sum_residual = gs.sum_res;
+            if (profile) {
+                // algorithmic bytes are per scan; the launch and its time are shared by the batch and reported on scan 0
+                o.algo_bytes = (long long)gs.iter * (long long)n[s] * per_point_iter_bytes + (long long)(gs.cand_total + 0.5) * per_cand_bytes;
+                o.kernel_ms = s == 0 ? kernel_ms : 0.f;
+                o.kernel_launches = s == 0 ? 1 : 0;
+            }
+        }
+    }
+    std::memcpy(T_final, T, sizeof(T_final));
+    log_n = h_state[0].iter < log_cap ? h_state[0].iter : log_cap;
+    if (std::getenv("FLS_DEBUG_TIMING")) {
+        const GnState& g0 = h_state[0];
+        std::fprintf(stderr, "[fls timing] batch %d  scan 0: iters %d  candidates/pt-iter %.1f\n", B, g0.iter,
+                     g0.cand_total / (double)((long long)n[0] * (g0.iter > 0 ? g0.iter : 1)));
+        for (int it = 0; it < g0.iter && it < 16; ++it) {
+            const unsigned long long* d = g0.dbg[it];
+            std::fprintf(stderr, "[fls timing] it %d: until all rows in %.1f us | fold %.1f us | solve+publish %.1f us | to next start %.1f us\n", it,
+                         (d[1] - d[0]) * 1e-3, (d[2] - d[1]) * 1e-3, (d[3] - d[2]) * 1e-3,
+                         (it + 1 < g0.iter && it + 1 < 16) ? (g0.dbg[it + 1][0] - d[3]) * 1e-3 : 0.0);
+        }
+    }
+    return FLS_OK;
+}
+
+int Handle::match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st) {
+    const float4* scans[1] = {d_src};
+    const size_t ns[1] = {n};
+    int conv = 0;
+    const int rc = match_ivox_batch(1, scans, ns, T, &conv, st);
     if (rc != FLS_OK) return rc;
+    if (converged) *converged = conv;
+    const int ni = (int)n;
     if (h_state->converged && !cfg.localization_mode) {
         // :205-206 — the scan enters the map through the cached-5-NN rule (body-frame points, final pose)  [quirk 8]
         stage.reserve(n + 1);
@@ -861,6 +976,63 @@ int fls_match_device(fls_handle* hh, const void* d_points, size_t n, double T[16
     const float4* d = static_cast<const float4*>(d_points);
     if (h->cfg.method == FLS_LOAM_FULL) return FLS_ERR_UNSUPPORTED;  // two feature clouds: use fls_match
     return match_dispatch(h, d, n, d, n, nullptr, 0, T, converged, st);
+    FLS_CATCH
+}
+
+int fls_match_batch(fls_handle* hh, int n_scans, const void* const* planar, const size_t* n, size_t stride, double* T, int* converged,
+                    fls_match_stats* st) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || !planar || !n || !T || n_scans < 1 || n_scans > fls::kMaxBatch || !stride_ok(stride)) return FLS_ERR_INVALID_ARG;
+    if (h->cfg.method != FLS_P2PLANE_IVOX) return FLS_ERR_UNSUPPORTED;
+    // scans of one batch are matched against the same map state: only meaningful when Match does not modify the map
+    if (n_scans > 1 && !h->cfg.localization_mode) return FLS_ERR_UNSUPPORTED;
+    FLS_TRY
+    if (st) std::memset(st, 0, sizeof(*st) * (size_t)n_scans);
+    h->begin_call();
+    size_t total = 0;
+    for (int s = 0; s < n_scans; ++s) {
+        if (!planar[s] && n[s]) return FLS_ERR_INVALID_ARG;
+        total += n[s];
+    }
+    h->src.reserve(total + 1);
+    if (stride != FLS_LAYOUT_PACKED) h->raw.reserve(total * stride);
+    const float4* ptrs[fls::kMaxBatch];
+    size_t off = 0;
+    for (int s = 0; s < n_scans; ++s) {
+        ptrs[s] = h->src.p + off;
+        if (n[s]) {
+            if (stride == FLS_LAYOUT_PACKED) {
+                FLS_CUDA(cudaMemcpyAsync(h->src.p + off, planar[s], n[s] * 16, cudaMemcpyHostToDevice, h->stream));
+            } else {
+                FLS_CUDA(cudaMemcpyAsync(h->raw.p + off * stride, planar[s], n[s] * stride, cudaMemcpyHostToDevice, h->stream));
+                fls::launch_repack(h->raw.p + off * stride, n[s], stride, h->src.p + off, h->stream);
+                h->launches++;
+            }
+            h->h2d_bytes += (long long)(n[s] * stride);
+        }
+        off += n[s];
+    }
+    if (n_scans == 1) return h->match_p2plane_ivox(ptrs[0], n[0], T, converged, st);
+    return h->match_ivox_batch(n_scans, ptrs, n, T, converged, st);
+    FLS_CATCH
+}
+
+int fls_match_batch_device(fls_handle* hh, int n_scans, const void* const* d_planar, const size_t* n, double* T, int* converged,
+                           fls_match_stats* st) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || !d_planar || !n || !T || n_scans < 1 || n_scans > fls::kMaxBatch) return FLS_ERR_INVALID_ARG;
+    if (h->cfg.method != FLS_P2PLANE_IVOX) return FLS_ERR_UNSUPPORTED;
+    if (n_scans > 1 && !h->cfg.localization_mode) return FLS_ERR_UNSUPPORTED;
+    FLS_TRY
+    if (st) std::memset(st, 0, sizeof(*st) * (size_t)n_scans);
+    h->begin_call();
+    const float4* ptrs[fls::kMaxBatch];
+    for (int s = 0; s < n_scans; ++s) {
+        if (!d_planar[s] && n[s]) return FLS_ERR_INVALID_ARG;
+        ptrs[s] = static_cast<const float4*>(d_planar[s]);
+    }
+    if (n_scans == 1) return h->match_p2plane_ivox(ptrs[0], n[0], T, converged, st);
+    return h->match_ivox_batch(n_scans, ptrs, n, T, converged, st);
     FLS_CATCH
 }
 

@@ -32,6 +32,10 @@ struct Handle {
     DevBuf<int> sync_buf;  // work / arrive counters + release flag of the persistent LOAM kernel
     DevBuf<uint4> ll_rows;      // LL hand-over records of the persistent LOAM-iVox kernel: [grid][32] rows + pose record
     unsigned match_epoch = 0;   // tag prefix of those records
+    unsigned char* h_batch = nullptr;  // pinned staging of the per-batch tables (poses, offsets, scan descriptors, CTA map, pointers)
+    size_t h_batch_cap = 0;
+    DevBuf<unsigned char> d_batch;
+    std::vector<long long> batch_n;    // points per scan of the last batch
     DevBuf<GnState> state;
     GnState* h_state = nullptr;  // pinned
     DevBuf<fls_iter_log> log;
@@ -100,6 +104,8 @@ struct Handle {
 
     int add_cloud_ivox(const void* pts, size_t n, size_t stride);
     int match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st);
+    // n_scans independent scans against the (static) map in ONE persistent launch; d_scans: host array of device pointers
+    int match_ivox_batch(int n_scans, const float4* const* d_scans, const size_t* n, double* T, int* converged, fls_match_stats* st);
 
     int add_cloud_ndt(const float4* d_cloud, size_t n);
     int match_ndt(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st);

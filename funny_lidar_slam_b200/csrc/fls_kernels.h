@@ -12,28 +12,45 @@ static constexpr int kNdtBlock = 128;
 static constexpr int kIcpBlock = 128;
 static constexpr int kLoamBlock = 128;
 
-// whole-loop arguments of the persistent LoamPointToPlaneIVOX kernel (K1 + fused K6)
-struct P2PlaneLoopArgs {
-    const float4* __restrict__ src;  // body-frame scan in Morton order of the query voxel, packed float4
+static constexpr int kMaxBatch = 64;  // scans per fls_match_batch call
+
+struct PoseArg {
+    double R[9];  // row-major
+    double t[3];
+};
+
+// One scan of a batch (device-resident descriptor read by the persistent LoamPointToPlaneIVOX kernel)
+struct P2PlaneScan {
+    const float4* src;  // body-frame scan in Morton order of the query voxel, packed float4
     int n;
+    int cta_begin, cta_count;  // this scan's CTAs: [cta_begin, cta_begin + cta_count); the first one folds and solves
+    unsigned tag_base;         // Match epoch << 8 (hand-over tags, fls_gn.cuh)
+    GnState* state;
+    float4* rec0;  // persistent per-point record: J0..J3
+    float4* rec1;  //                              J4, J5, |d|, 1
+    unsigned char* flags;
+    uint4* rows;     // [cta_count][32] LL records {lo, tag, hi, tag}: one per CTA and sum
+    uint4* ll_pose;  // [kLlPoseLen] LL records: next pose + stop word, published by the folding CTA
+    fls_iter_log* log;
+};
+
+// whole-loop arguments of the persistent LoamPointToPlaneIVOX kernel (K1 + fused K6); one launch = a batch of scans
+struct P2PlaneLoopArgs {
     IvoxView map;
     double plane_thres;
-    GnState* state;
-    float4* __restrict__ rec0;  // persistent per-point record: J0..J3
-    float4* __restrict__ rec1;  //                              J4, J5, |d|, 1
-    unsigned char* __restrict__ flags;
-    uint4* rows;        // [grid][32] LL records {lo, tag, hi, tag}: one per CTA and sum (fls_gn.cuh)
-    uint4* ll_pose;     // [kLlPoseLen] LL records: next pose + stop word, published by the folding CTA
-    unsigned tag_base;  // Match epoch << 8
     GnParams gp;
-    fls_iter_log* log;
     int log_cap;
+    const P2PlaneScan* scans;  // [n_scans]
+    const int* cta_scan;       // [grid] scan index of every CTA
 };
-int p2plane_grid(int n, int device);
-int p2plane_chunks(int n);            // warp-sized (32-point) work chunks
+int p2plane_block();                   // threads per CTA of the selected kernel shape
+int p2plane_max_grid(int device);      // co-resident CTAs
+int p2plane_chunks(int n);             // warp-sized (32-point) work chunks
+int p2plane_grid(int n, int device, int share = 1);  // CTAs for one scan when `share` scans split the device
 void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st);
-void prepare_queries(const float4* d_src, int n, const double* T_colmajor, GnState* d_state, const IvoxView& map, unsigned char* d_flags,
-                     float4* d_sorted, BuildScratch& sc, cudaStream_t st, int* launches);
+// d_scan_ptrs[n_scans]: device pointers of the scans; d_offsets[n_scans + 1]: their positions in the batch; d_poses / d_states[n_scans]
+void prepare_queries(const float4* const* d_scan_ptrs, int n_total, const int* d_offsets, int n_scans, const PoseArg* d_poses, GnState* d_states,
+                     const IvoxView& map, unsigned char* d_flags, float4* d_sorted, BuildScratch& sc, cudaStream_t st, int* launches);
 // LOAM-iVox Match-internal AddCloudToLocalMap: classify + compact the points that enter the map (d_world, d_out: n records)
 size_t select_ivox_inserts(const IvoxView& map, const float4* d_src, int n, const double* R_prev, const double* t_prev, const double* R_fin,
                            const double* t_fin, double filter, float4* d_world, float4* d_out, BuildScratch& sc, cudaStream_t st, int* launches);

@@ -214,11 +214,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
     __shared__ double s_red[W][32];
     __shared__ int s_done;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_chunks = (a.n + 31) >> 5;  // warp-sized chunks
-    const int n_warps = (int)gridDim.x * W;
-    // CTA 0 folds and solves; chunks are dealt from the highest CTA index down so that CTA 0 is the one that stays idle
-    // whenever the grid has more warps than the scan has chunks (p2plane_grid adds one CTA for that purpose)
-    const int first_chunk = ((int)gridDim.x - 1 - (int)blockIdx.x) * W + warp;
+    // One launch serves a batch of independent scans: this CTA belongs to scan `sc` and is CTA `cta` of its `G`.  Every
+    // scan runs its own Gauss-Newton loop with its own hand-over records; scans never synchronise with each other, so
+    // while one scan's CTAs wait for their solve the SM keeps working on the CTAs of another.
+    const P2PlaneScan sc = a.scans[a.cta_scan[blockIdx.x]];
+    const int cta = (int)blockIdx.x - sc.cta_begin, G = sc.cta_count;
+    const int n_chunks = (sc.n + 31) >> 5;  // warp-sized chunks
+    const int n_warps = G * W;
+    // CTA 0 of the scan folds and solves; chunks are dealt from the highest CTA index down so that CTA 0 is the one that
+    // stays idle whenever the scan has more warps than chunks (p2plane_grid adds one CTA for that purpose)
+    const int first_chunk = (G - 1 - cta) * W + warp;
 
     // which product of record columns lane k accumulates: sum_k = sgn * sum_p rec[p][ca] * rec[p][cb]
     int ca = kRecOne, cb = kRecOne;
@@ -242,13 +247,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
         sgn = 0.0;
     }
 
-    if (threadIdx.x < 9) s_pose[threadIdx.x] = __ldcg(&a.state->R[threadIdx.x]);
-    else if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(&a.state->t[threadIdx.x - 9]);
+    if (threadIdx.x < 9) s_pose[threadIdx.x] = __ldcg(&sc.state->R[threadIdx.x]);
+    else if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(&sc.state->t[threadIdx.x - 9]);
     __syncthreads();
 
     for (int it = 0; it < a.gp.max_iterations; ++it) {
-        const unsigned tag = a.tag_base | (unsigned)(it + 1);
-        if (blockIdx.x == 0 && threadIdx.x == 0 && it < 16) a.state->dbg[it][0] = globaltimer_ns();
+        const unsigned tag = sc.tag_base | (unsigned)(it + 1);
+        if (cta == 0 && threadIdx.x == 0 && it < 16) sc.state->dbg[it][0] = globaltimer_ns();
 
         double acc = 0.0;  // lane k's running sum over every chunk of this warp
         // warp-granular work loop, static round-robin over 32-point chunks: no barrier, no atomics inside
@@ -258,15 +263,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
             const int i = (chunk << 5) + lane;
             double J[6] = {0, 0, 0, 0, 0, 0}, ad = 0.0, vflag = 0.0;
             unsigned n_cand = 0, n_fb = 0;
-            if (i < a.n) {
-                const float4 sp = a.src[i];
+            if (i < sc.n) {
+                const float4 sp = sc.src[i];
                 bool use = p2plane_point(a.map, sp, s_pose, a.plane_thres, J, ad, n_cand, n_fb);
                 if (use) {
-                    a.rec0[i] = make_float4((float)J[0], (float)J[1], (float)J[2], (float)J[3]);
-                    a.rec1[i] = make_float4((float)J[4], (float)J[5], (float)ad, 1.0f);
-                    a.flags[i] = 1;
-                } else if (a.flags[i]) {  // stale contribution [quirk 1]
-                    const float4 r0 = a.rec0[i], r1 = a.rec1[i];
+                    sc.rec0[i] = make_float4((float)J[0], (float)J[1], (float)J[2], (float)J[3]);
+                    sc.rec1[i] = make_float4((float)J[4], (float)J[5], (float)ad, 1.0f);
+                    sc.flags[i] = 1;
+                } else if (sc.flags[i]) {  // stale contribution [quirk 1]
+                    const float4 r0 = sc.rec0[i], r1 = sc.rec1[i];
                     J[0] = r0.x; J[1] = r0.y; J[2] = r0.z; J[3] = r0.w; J[4] = r1.x; J[5] = r1.y;
                     ad = r1.z;
                     use = true;
@@ -297,16 +302,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
             double v = 0;
 #pragma unroll
             for (int w = 0; w < W; ++w) v += s_red[w][lane];
-            ll_store(a.rows + (size_t)blockIdx.x * 32 + lane, v, tag);
+            ll_store(sc.rows + (size_t)cta * 32 + lane, v, tag);
         }
-        if (blockIdx.x == 0) {
+        if (cta == 0) {
             // ---- fold: warp w owns rows w, w+W, ...; every sweep re-reads all of them (independent loads, one L2 round
             // trip) until each carries this iteration's tag, then the sums are taken in a fixed order — bitwise
             // reproducible, and the fold is finished one sweep after the slowest CTA's row lands
             GnPre pre;
-            if (threadIdx.x == 0) gn_load(a.state, pre);  // off the critical path: the state is stable until gn_step below
+            if (threadIdx.x == 0) gn_load(sc.state, pre);  // off the critical path: the state is stable until gn_step below
             __syncthreads();  // s_red is free again
-            const int nrows = (int)gridDim.x;
+            const int nrows = G;
             double sum;
             for (;;) {
                 bool ok = true;
@@ -314,30 +319,30 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
                 int r = warp;
                 for (; r + 7 * W < nrows; r += 8 * W) {  // 8 independent 16-byte loads in flight per lane
                     double v0, v1, v2, v3, v4, v5, v6, v7;
-                    const bool k0 = ll_load(a.rows + (size_t)r * 32 + lane, tag, v0);
-                    const bool k1 = ll_load(a.rows + (size_t)(r + W) * 32 + lane, tag, v1);
-                    const bool k2 = ll_load(a.rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
-                    const bool k3 = ll_load(a.rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
-                    const bool k4 = ll_load(a.rows + (size_t)(r + 4 * W) * 32 + lane, tag, v4);
-                    const bool k5 = ll_load(a.rows + (size_t)(r + 5 * W) * 32 + lane, tag, v5);
-                    const bool k6 = ll_load(a.rows + (size_t)(r + 6 * W) * 32 + lane, tag, v6);
-                    const bool k7 = ll_load(a.rows + (size_t)(r + 7 * W) * 32 + lane, tag, v7);
+                    const bool k0 = ll_load(sc.rows + (size_t)r * 32 + lane, tag, v0);
+                    const bool k1 = ll_load(sc.rows + (size_t)(r + W) * 32 + lane, tag, v1);
+                    const bool k2 = ll_load(sc.rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
+                    const bool k3 = ll_load(sc.rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
+                    const bool k4 = ll_load(sc.rows + (size_t)(r + 4 * W) * 32 + lane, tag, v4);
+                    const bool k5 = ll_load(sc.rows + (size_t)(r + 5 * W) * 32 + lane, tag, v5);
+                    const bool k6 = ll_load(sc.rows + (size_t)(r + 6 * W) * 32 + lane, tag, v6);
+                    const bool k7 = ll_load(sc.rows + (size_t)(r + 7 * W) * 32 + lane, tag, v7);
                     ok = ok && k0 && k1 && k2 && k3 && k4 && k5 && k6 && k7;
                     a0 += v0; a1 += v1; a2 += v2; a3 += v3;
                     a0 += v4; a1 += v5; a2 += v6; a3 += v7;
                 }
                 for (; r + 3 * W < nrows; r += 4 * W) {
                     double v0, v1, v2, v3;
-                    const bool k0 = ll_load(a.rows + (size_t)r * 32 + lane, tag, v0);
-                    const bool k1 = ll_load(a.rows + (size_t)(r + W) * 32 + lane, tag, v1);
-                    const bool k2 = ll_load(a.rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
-                    const bool k3 = ll_load(a.rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
+                    const bool k0 = ll_load(sc.rows + (size_t)r * 32 + lane, tag, v0);
+                    const bool k1 = ll_load(sc.rows + (size_t)(r + W) * 32 + lane, tag, v1);
+                    const bool k2 = ll_load(sc.rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
+                    const bool k3 = ll_load(sc.rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
                     ok = ok && k0 && k1 && k2 && k3;
                     a0 += v0; a1 += v1; a2 += v2; a3 += v3;
                 }
                 for (; r < nrows; r += W) {
                     double v0;
-                    ok = ok && ll_load(a.rows + (size_t)r * 32 + lane, tag, v0);
+                    ok = ok && ll_load(sc.rows + (size_t)r * 32 + lane, tag, v0);
                     a0 += v0;
                 }
                 sum = (a0 + a1) + (a2 + a3);
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
             s_red[warp][lane] = sum;
             __syncthreads();
             if (warp == 0) {
-                if (lane == 0 && it < 16) a.state->dbg[it][1] = globaltimer_ns();
+                if (lane == 0 && it < 16) sc.state->dbg[it][1] = globaltimer_ns();
                 double t = 0;
 #pragma unroll
                 for (int w = 0; w < W; ++w) t += s_red[w][lane];
@@ -355,16 +360,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
                 s_red[0][lane] = t;
                 __syncwarp();
                 if (lane == 0) {
-                    if (it < 16) a.state->dbg[it][2] = globaltimer_ns();
-                    gn_step_pre(a.state, pre, s_red[0], a.gp, a.log, a.log_cap, nullptr, 0, a.ll_pose, tag);
-                    if (it < 16) a.state->dbg[it][3] = globaltimer_ns();
+                    if (it < 16) sc.state->dbg[it][2] = globaltimer_ns();
+                    gn_step_pre(sc.state, pre, s_red[0], a.gp, sc.log, a.log_cap, nullptr, 0, sc.ll_pose, tag);
+                    if (it < 16) sc.state->dbg[it][3] = globaltimer_ns();
                 }
             }
         }
         // ---- next pose: everybody polls the LL pose record (12 values + the stop word) -----------------------------------
         if (threadIdx.x < 13) {
             double v;
-            while (!ll_load(a.ll_pose + threadIdx.x, tag, v)) __nanosleep(100);
+            while (!ll_load(sc.ll_pose + threadIdx.x, tag, v)) __nanosleep(100);
             if (threadIdx.x < 12) s_pose[threadIdx.x] = v;
             else s_done = v != 0.0;
         }
@@ -383,48 +388,54 @@ __device__ __forceinline__ unsigned spread_bits3(unsigned v) {  // up to 10 bits
     return v;
 }
 
-struct PoseArg {
-    double R[9];  // row-major
-    double t[3];
-};
-
-// Per-Match preparation in ONE launch: initialise the GN state from the caller's pose, clear the hand-over counters
-// and the per-point valid flags [quirk 1: reset once per Match], and compute the locality key of every query.
-// Key = 3-D Morton of the low 4 bits per axis of the query's voxel at the initial pose (an 8 m cube) topped with
-// `hbits` more bits each of x and y; wrap-around beyond that only costs locality, never correctness.
-// key_bits = 12 + 2*hbits: 24 bits = three 8-bit radix passes, 16 bits = two.
-__global__ void p2plane_prep_kernel(const float4* __restrict__ src, int n, PoseArg pose, float inv_res, int hbits, unsigned* __restrict__ keys,
-                                    unsigned* __restrict__ idx, unsigned char* __restrict__ flags, GnState* __restrict__ s,
+// Per-batch preparation in ONE launch: for every scan initialise its GN state from the caller's pose, clear the per-point
+// valid flags [quirk 1: reset once per Match], and compute the locality key of every query.
+// Key = scan index on top of the 3-D Morton code of the low 4 bits per axis of the query's voxel at the initial pose (an
+// 8 m cube) and `hbits` more bits each of x and y; wrap-around beyond that only costs locality, never correctness.
+// morton bits = 12 + 2*hbits (16: two 8-bit radix passes); the scan bits keep every scan contiguous after the sort.
+__global__ void p2plane_prep_kernel(const float4* const* __restrict__ scan_ptrs, int n_total, const int* __restrict__ offsets, int n_scans,
+                                    const PoseArg* __restrict__ poses, float inv_res, int hbits, unsigned* __restrict__ keys,
+                                    unsigned* __restrict__ idx, unsigned char* __restrict__ flags, GnState* __restrict__ states,
                                     const HashSlot* __restrict__ ctab, unsigned cmask, const float4* __restrict__ lists) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x == 0) {
-        if (threadIdx.x == 0) {
-            for (int k = 0; k < 9; ++k) s->R[k] = s->R0[k] = s->Rprev[k] = pose.R[k];
-            for (int k = 0; k < 3; ++k) s->t[k] = s->t0[k] = s->tprev[k] = pose.t[k];
-            s->last_rot = s->last_pos = 0.0;
-            s->sum_res = 0;
-            s->cand_total = s->hits_total = 0;
-            s->n_valid = 0;
-            s->iter = 0;
-            s->done = 0;
-            s->converged = 0;
-            s->failed = 0;
-        }
+    if (blockIdx.x == 0 && (int)threadIdx.x < n_scans) {
+        GnState* s = states + threadIdx.x;
+        const PoseArg& pose = poses[threadIdx.x];
+        for (int k = 0; k < 9; ++k) s->R[k] = s->R0[k] = s->Rprev[k] = pose.R[k];
+        for (int k = 0; k < 3; ++k) s->t[k] = s->t0[k] = s->tprev[k] = pose.t[k];
+        s->last_rot = s->last_pos = 0.0;
+        s->sum_res = 0;
+        s->cand_total = s->hits_total = 0;
+        s->n_valid = 0;
+        s->iter = 0;
+        s->done = 0;
+        s->converged = 0;
+        s->failed = 0;
     }
-    if (i >= n) return;
+    if (i >= n_total) return;
     flags[i] = 0;
-    const float4 sp = src[i];
-    const double* R = pose.R;
-    const float qx = xform_row_d(R[0], R[1], R[2], pose.t[0], sp.x, sp.y, sp.z);
-    const float qy = xform_row_d(R[3], R[4], R[5], pose.t[1], sp.x, sp.y, sp.z);
-    const float qz = xform_row_d(R[6], R[7], R[8], pose.t[2], sp.x, sp.y, sp.z);
+    int sid = 0;  // scan of point i: offsets is ascending, n_scans <= kMaxBatch
+    {
+        int lo = 0, hi = n_scans;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(offsets + mid) <= i) lo = mid;
+            else hi = mid;
+        }
+        sid = lo;
+    }
+    const float4 sp = scan_ptrs[sid][i - __ldg(offsets + sid)];
+    const PoseArg& pose = poses[sid];
+    const float qx = xform_row_d(__ldg(&pose.R[0]), __ldg(&pose.R[1]), __ldg(&pose.R[2]), __ldg(&pose.t[0]), sp.x, sp.y, sp.z);
+    const float qy = xform_row_d(__ldg(&pose.R[3]), __ldg(&pose.R[4]), __ldg(&pose.R[5]), __ldg(&pose.t[1]), sp.x, sp.y, sp.z);
+    const float qz = xform_row_d(__ldg(&pose.R[6]), __ldg(&pose.R[7]), __ldg(&pose.R[8]), __ldg(&pose.t[2]), sp.x, sp.y, sp.z);
     const unsigned kx = (unsigned)ivox_coord(qx, inv_res), ky = (unsigned)ivox_coord(qy, inv_res), kz = (unsigned)ivox_coord(qz, inv_res);
     const unsigned lo = spread_bits3(kx & 15u) | (spread_bits3(ky & 15u) << 1) | (spread_bits3(kz & 15u) << 2);  // 12 bits
     const unsigned hm = (1u << hbits) - 1u;
     const unsigned hx = (kx >> 4) & hm, hy = (ky >> 4) & hm;
     unsigned hi = 0;
     for (int b = 0; b < hbits; ++b) hi |= (((hx >> b) & 1u) << (2 * b)) | (((hy >> b) & 1u) << (2 * b + 1));
-    keys[i] = lo | (hi << 12);
+    keys[i] = lo | (hi << 12) | ((unsigned)sid << (12 + 2 * hbits));
     idx[i] = (unsigned)i;
     // Warm L2 for the first iteration: the candidate run of the voxel this point starts in is requested now and arrives
     // while the radix sort runs (the GN kernel is latency-bound on exactly these lines when they come from HBM).  One
@@ -444,9 +455,19 @@ __global__ void p2plane_prep_kernel(const float4* __restrict__ src, int n, PoseA
     }
 }
 
-__global__ void gather4_kernel(const float4* __restrict__ src, const unsigned* __restrict__ idx, int n, float4* __restrict__ dst) {
+// dst[i] = point idx[i] of the batch, where the batch is the concatenation of the scans behind `scan_ptrs`
+__global__ void gather4_kernel(const float4* const* __restrict__ scan_ptrs, const int* __restrict__ offsets, int n_scans,
+                               const unsigned* __restrict__ idx, int n, float4* __restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[idx[i]];
+    if (i >= n) return;
+    const int g = (int)idx[i];
+    int lo = 0, hi = n_scans;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid) <= g) lo = mid;
+        else hi = mid;
+    }
+    dst[i] = scan_ptrs[lo][g - __ldg(offsets + lo)];
 }
 
 __global__ void ivox_knn_test_kernel(IvoxView map, const float4* __restrict__ q, int n, float4* __restrict__ out, int* __restrict__ found) {
@@ -573,10 +594,11 @@ int p2plane_max_grid(int device) {
 
 int p2plane_chunks(int n) { return (n + 31) / 32; }
 
-int p2plane_grid(int n, int device) {
+int p2plane_grid(int n, int device, int share) {
     const int W = p2plane_block() / 32;
     const int need = (p2plane_chunks(n) + W - 1) / W;
-    const int cap = p2plane_max_grid(device);
+    int cap = p2plane_max_grid(device) / (share > 0 ? share : 1);
+    if (cap < 1) cap = 1;
     const int g = need + 1 < cap ? need + 1 : cap;  // + the folding CTA (stays without chunks when there is room)
     return g > 0 ? g : 1;
 }
@@ -590,38 +612,36 @@ void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st) {
         FLS_CUDA(cudaLaunchCooperativeKernel(P2PlaneShape<768>::fn(), dim3(grid), dim3(768), params, P2PlaneShape<768>::smem(), st));
 }
 
-// Per-Match preparation: state init + counter / flag reset + locality keys (one kernel), then order the scan by the
-// voxel each point falls into at the initial pose (CUB radix sort of {key, index}, gather).
-void prepare_queries(const float4* d_src, int n, const double* T_colmajor, GnState* d_state, const IvoxView& map, unsigned char* d_flags,
-                     float4* d_sorted, BuildScratch& sc, cudaStream_t st, int* launches) {
-    const float inv_res = map.inv_res;
-    const int m = n > 0 ? n : 1;
+// Per-batch preparation: state init + flag reset + locality keys (one kernel), then order every scan by the voxel each
+// point falls into at its initial pose (ONE CUB radix sort of {scan | key, index} over the whole batch, gather).
+void prepare_queries(const float4* const* d_scan_ptrs, int n_total, const int* d_offsets, int n_scans, const PoseArg* d_poses, GnState* d_states,
+                     const IvoxView& map, unsigned char* d_flags, float4* d_sorted, BuildScratch& sc, cudaStream_t st, int* launches) {
+    const int m = n_total > 0 ? n_total : 1;
     sc.k32a.reserve(m);
     sc.k32b.reserve(m);
     sc.idx.reserve(m);
     sc.idx_sorted.reserve(m);
-    PoseArg pose;
-    for (int r = 0; r < 3; ++r) {
-        for (int c = 0; c < 3; ++c) pose.R[r * 3 + c] = T_colmajor[c * 4 + r];
-        pose.t[r] = T_colmajor[12 + r];
-    }
     const char* kb = std::getenv("FLS_SORT_KEY_BITS");
     // measured on B200 (tools/match_timing.py, 108 k points): 24-bit keys 186 us / Match, 16-bit keys 165 us — one
     // 12 us onesweep pass less, and the fused kernel is no slower (22.9 vs 23.8 us / iteration): an 8 m x 32 m x 32 m
     // Morton window is all the locality the L1 broadcast needs
     int key_bits = kb ? std::atoi(kb) : 16;
     if (key_bits != 16 && key_bits != 20 && key_bits != 24) key_bits = 16;
-    p2plane_prep_kernel<<<(m + 255) / 256, 256, 0, st>>>(d_src, n, pose, inv_res, (key_bits - 12) / 2, sc.k32a.p, sc.idx.p, d_flags, d_state,
-                                                        std::getenv("FLS_NO_PREFETCH") ? nullptr : map.ctab, map.cmask, map.lists);
+    int scan_bits = 0;
+    while ((1 << scan_bits) < n_scans) ++scan_bits;
+    p2plane_prep_kernel<<<(m + 255) / 256, 256, 0, st>>>(d_scan_ptrs, n_total, d_offsets, n_scans, d_poses, map.inv_res, (key_bits - 12) / 2, sc.k32a.p,
+                                                        sc.idx.p, d_flags, d_states, std::getenv("FLS_NO_PREFETCH") ? nullptr : map.ctab,
+                                                        map.cmask, map.lists);
     if (launches) *launches += 1;
-    if (n <= 0) return;
+    if (n_total <= 0) return;
+    const int sort_bits = key_bits + scan_bits;
     size_t t1 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t1, sc.k32a.p, sc.k32b.p, sc.idx.p, sc.idx_sorted.p, n, 0, key_bits, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, sc.k32a.p, sc.k32b.p, sc.idx.p, sc.idx_sorted.p, n_total, 0, sort_bits, st);
     sc.cub_tmp.reserve(t1 + 256);
     size_t tb = sc.cub_tmp.cap;
-    FLS_CUDA(cub::DeviceRadixSort::SortPairs(sc.cub_tmp.p, tb, sc.k32a.p, sc.k32b.p, sc.idx.p, sc.idx_sorted.p, n, 0, key_bits, st));
-    gather4_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_src, sc.idx_sorted.p, n, d_sorted);
-    if (launches) *launches += 2 + key_bits / 8 + 1;
+    FLS_CUDA(cub::DeviceRadixSort::SortPairs(sc.cub_tmp.p, tb, sc.k32a.p, sc.k32b.p, sc.idx.p, sc.idx_sorted.p, n_total, 0, sort_bits, st));
+    gather4_kernel<<<(n_total + 255) / 256, 256, 0, st>>>(d_scan_ptrs, d_offsets, n_scans, sc.idx_sorted.p, n_total, d_sorted);
+    if (launches) *launches += 2 + (sort_bits + 7) / 8 + 1;
 }
 
 // Returns the number of points selected for insertion (class 1 then class 2, input order) in d_out; synchronises the stream.

@@ -91,6 +91,43 @@ class Registration:
         check(rc, "fls_fitness")
         return float(out.value)
 
+    # -- batched Match (throughput entry; LoamPointToPlaneIVOX in localization mode) -----------------------------
+    def match_batch(self, scans, Ts):
+        """scans: list of (n,4)/(n,8) host clouds; Ts: (B,4,4) float64 initial poses.  Returns (converged[B], T[B,4,4]);
+        self.last_batch_stats holds the per-scan fls_match_stats (call-level timings on element 0)."""
+        B = len(scans)
+        ptrs, ns, keep, stride = [], [], [], None
+        for c in scans:
+            p, n, s, a = _cloud(c)
+            if stride is not None and s != stride:
+                raise ValueError("all scans of one batch must share a layout")
+            stride = s
+            ptrs.append(p)
+            ns.append(n)
+            keep.append(a)
+        Tc = np.ascontiguousarray(np.transpose(np.asarray(Ts, np.float64), (0, 2, 1))).copy()  # Eigen column-major per pose
+        conv = (C.c_int * B)()
+        st = (FlsMatchStats * B)()
+        arr_p = (C.c_void_p * B)(*ptrs)
+        arr_n = (C.c_size_t * B)(*ns)
+        check(lib().fls_match_batch(self._h, B, arr_p, arr_n, stride, Tc.ctypes.data_as(C.c_void_p), conv, st), "fls_match_batch")
+        self.last_batch_stats = list(st)
+        self.last_stats = st[0]
+        return np.array(conv[:], bool), np.transpose(Tc, (0, 2, 1)).copy()
+
+    def match_batch_device(self, d_ptrs, ns, Ts):
+        """Same with device-resident packed float4 scans: d_ptrs = list of device addresses, ns = point counts."""
+        B = len(d_ptrs)
+        Tc = np.ascontiguousarray(np.transpose(np.asarray(Ts, np.float64), (0, 2, 1))).copy()
+        conv = (C.c_int * B)()
+        st = (FlsMatchStats * B)()
+        arr_p = (C.c_void_p * B)(*[int(p) for p in d_ptrs])
+        arr_n = (C.c_size_t * B)(*[int(n) for n in ns])
+        check(lib().fls_match_batch_device(self._h, B, arr_p, arr_n, Tc.ctypes.data_as(C.c_void_p), conv, st), "fls_match_batch_device")
+        self.last_batch_stats = list(st)
+        self.last_stats = st[0]
+        return np.array(conv[:], bool), np.transpose(Tc, (0, 2, 1)).copy()
+
     # -- device-resident scan (bench `value` leg) ---------------------------------------------------------
     def match_device(self, d_ptr: int, n: int, T: np.ndarray) -> bool:
         Tc = np.ascontiguousarray(np.asarray(T, np.float64).T).copy()

@@ -172,6 +172,16 @@ int fls_match_device(fls_handle* h, const void* d_points, size_t n, double T_col
 int fls_fitness(fls_handle* h, float max_range, float* score);
 
 /* per-iteration log of the last fls_match (needs FLS_FLAG_ITER_LOG); returns the number of entries written */
+/* Batched Match for throughput (the benchmark entry SURVEY.md §8b names): `n_scans` (<= 64) independent scans, each with its
+ * own in-out pose T[s*16 .. s*16+15], converged[s] and stats[s], matched against the same map in ONE persistent launch.
+ * Implemented for FLS_P2PLANE_IVOX; more than one scan requires localization_mode (Match must not modify the map).
+ * Call-level figures (gpu_ms, gpu_launches, byte counts, kernel_ms) are reported in stats[0]; per-scan fields everywhere.
+ * Results are identical to n_scans separate fls_match calls.  The _device variant takes device pointers to packed float4 scans. */
+int fls_match_batch(fls_handle* h, int n_scans, const void* const* planar, const size_t* n, size_t stride_bytes, double* T_colmajor,
+                    int* converged, fls_match_stats* stats);
+int fls_match_batch_device(fls_handle* h, int n_scans, const void* const* d_planar, const size_t* n, double* T_colmajor, int* converged,
+                           fls_match_stats* stats);
+
 int fls_get_iter_log(const fls_handle* h, fls_iter_log* out, int capacity);
 
 int fls_get_map_info(const fls_handle* h, fls_map_info* out);

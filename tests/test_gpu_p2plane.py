@@ -158,3 +158,52 @@ def test_external_add_after_first_is_rejected_in_mapping_mode(scene16):
     g.AddCloudToLocalMap([scene16["map"]])
     with pytest.raises(FlsError):  # upstream would run the insertion rule on caches of a Match that never happened
         g.AddCloudToLocalMap([scene16["map"]])
+
+
+def test_batch_equals_separate_matches(world, traj):
+    """fls_match_batch: B scans with different sizes, poses and iteration counts in ONE launch — every result must be
+    the one a separate Match returns (same kernel; only the number of CTAs per scan, hence the fp64 summation order,
+    differs: poses agree to ~1e-12)."""
+    from funny_lidar_slam_b200.registration import PointcloudCluster, Registration
+    from oracle import pyoracle as orc
+    mp = synth.make_map_from_scans(world, traj[0:12:2], "vlp16", leaf=0.3)
+    cfg = default_config(FLS_P2PLANE_IVOX)
+    g = Registration(cfg)
+    g.AddCloudToLocalMap([mp])
+    scans, guesses = [], []
+    for k, (dp, dr, keep) in enumerate(((0.3, 3.0, 1), (0.05, 0.5, 1), (0.2, 1.0, 3), (0.1, 2.0, 1), (0.3, 0.2, 2))):
+        sc = synth.make_scan(world, traj[2 + k], "vlp16", seed=70 + k)["points"][::keep]
+        scans.append(np.ascontiguousarray(sc))
+        guesses.append(synth.perturb_pose(traj[2 + k], dpos=dp, drot_deg=dr, seed=k))
+    scans.append(scans[0][:40].copy())  # too few valid planes: Match fails, T still written
+    guesses.append(guesses[0].copy())
+    singles = []
+    for sc, gs in zip(scans, guesses):
+        T = gs.copy()
+        ok = g.Match(PointcloudCluster(planar_cloud=sc), T)
+        singles.append((ok, T, g.last_stats.iterations, g.last_stats.n_valid))
+    conv, Tb = g.match_batch(scans, np.stack(guesses))
+    its = [s.iterations for s in g.last_batch_stats]
+    assert len(set(its)) > 1  # the scans really stop at different iterations
+    for s, (ok, T, it, nv) in enumerate(singles):
+        assert bool(conv[s]) == ok and g.last_batch_stats[s].iterations == it and g.last_batch_stats[s].n_valid == nv, s
+        assert np.allclose(Tb[s], T, rtol=0, atol=1e-9), s
+    assert not conv[-1]
+    # and against the oracle for one of them
+    o = orc.Registration(cfg)
+    o.add_cloud(mp)
+    ok_o, To, _ = o.match(scans[2], guesses[2])
+    dt, dr_ = synth.pose_error(Tb[2], To)
+    assert dt < POS_TOL and dr_ < ROT_TOL
+    # pcl layout through the batch entry
+    conv2, Tb2 = g.match_batch([to_pcl(s) for s in scans], np.stack(guesses))
+    assert np.array_equal(Tb2, Tb) and np.array_equal(conv2, conv)  # same batch shape: bit-identical
+
+
+def test_batch_needs_static_map(scene16):
+    from funny_lidar_slam_b200._lib import FlsError
+    from funny_lidar_slam_b200.registration import Registration
+    g = Registration(default_config(FLS_P2PLANE_IVOX, localization_mode=0))
+    g.AddCloudToLocalMap([scene16["map"]])
+    with pytest.raises(FlsError):
+        g.match_batch([scene16["scan"], scene16["scan"]], np.stack([scene16["guess"], scene16["guess"]]))
