@@ -234,6 +234,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short K2/K3/K4 side measurements")
+    ap.add_argument("--batch", type=int, default=8, help="scans per GPU per step (one fls_match_batch call; BASELINE config 4 uses batches of 8)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -261,7 +262,8 @@ def main():
     if world_size > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n_scans = min(8, args.steps + args.warmup)
+    B = max(1, min(int(args.batch), 64))
+    n_scans = max(8, 2 * B)
     mp, scans, truths, guesses = build_scene(wl, rank, n_scans, log)
     cfg = make_cfg(wl, local_rank, len(mp))
     reg = Registration(cfg)
@@ -272,37 +274,39 @@ def main():
     d_scans = [torch.from_numpy(s).to(dev) for s in scans]
     h_scans = [torch.from_numpy(s).pin_memory() for s in scans]
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    # the one collective of a batch: {4x4 pose, converged, iterations} of this rank's scan, all-gathered over NCCL
-    pose_pin = torch.zeros(18, dtype=torch.float64).pin_memory()
-    pose_np = pose_pin.numpy()
-    pose_out = torch.zeros(18, dtype=torch.float64, device=dev)
-    gathered = torch.zeros(18 * world_size, dtype=torch.float64, device=dev) if world_size > 1 else None
+    # the one collective of a step: {4x4 pose, converged, iterations} of this rank's B scans, all-gathered over NCCL
+    pose_pin = torch.zeros(18 * B, dtype=torch.float64).pin_memory()
+    pose_np = pose_pin.numpy().reshape(B, 18)
+    pose_out = torch.zeros(18 * B, dtype=torch.float64, device=dev)
+    gathered = torch.zeros(18 * B * world_size, dtype=torch.float64, device=dev) if world_size > 1 else None
 
     def flush_l2():
         flush_buf.zero_()
         torch.cuda.synchronize()
 
-    def gather_batch(T, ok, r):
-        pose_np[:16] = T.reshape(-1)
-        pose_np[16] = 1.0 if ok else 0.0
-        pose_np[17] = r.last_stats.iterations
+    def gather_batch(Ts, oks, r):
+        pose_np[:, :16] = Ts.reshape(B, 16)
+        pose_np[:, 16] = oks
+        pose_np[:, 17] = [st.iterations for st in r.last_batch_stats]
         pose_out.copy_(pose_pin, non_blocking=True)
         dist.all_gather_into_tensor(gathered, pose_out)
 
+    def ids(i):
+        return [(i * B + j) % n_scans for j in range(B)]
+
     def step_device(i, r):
-        T = guesses[i % n_scans].copy()
-        ds = d_scans[i % n_scans]
-        ok = r.match_device(ds.data_ptr(), ds.shape[0], T)
+        k = ids(i)
+        oks, Ts = r.match_batch_device([d_scans[j].data_ptr() for j in k], [d_scans[j].shape[0] for j in k], np.stack([guesses[j] for j in k]))
         if world_size > 1:
-            gather_batch(T, ok, r)
-        return ok, T
+            gather_batch(Ts, oks, r)
+        return oks, Ts
 
     def step_host(i, r):
-        T = guesses[i % n_scans].copy()
-        ok = r.Match(PointcloudCluster(planar_cloud=h_scans[i % n_scans].numpy()), T)
+        k = ids(i)
+        oks, Ts = r.match_batch([h_scans[j].numpy() for j in k], np.stack([guesses[j] for j in k]))
         if world_size > 1:
-            gather_batch(T, ok, r)
-        return ok, T
+            gather_batch(Ts, oks, r)
+        return oks, Ts
 
     def barrier():
         if world_size > 1:
@@ -318,16 +322,17 @@ def main():
         for i in range(steps):
             flush_l2()
             e0.record()
-            ok, T = step_fn(warmup + i, r)
+            oks, Ts = step_fn(warmup + i, r)
             e1.record()
             torch.cuda.synchronize()
             tot_ms += e0.elapsed_time(e1)
-            st = r.last_stats
-            launches += st.gpu_launches
-            iters += st.iterations
-            h2d += st.h2d_bytes
-            d2h += st.d2h_bytes
-            errs.append(synth.pose_error(T, truths[(warmup + i) % n_scans]))
+            st = r.last_batch_stats
+            launches += st[0].gpu_launches
+            iters += sum(x.iterations for x in st)
+            h2d += st[0].h2d_bytes
+            d2h += st[0].d2h_bytes
+            for j, T in zip(ids(warmup + i), Ts):
+                errs.append(synth.pose_error(T, truths[j]))
         barrier()
         t = torch.tensor([tot_ms], dtype=torch.float64, device=dev)
         if world_size > 1:
@@ -349,10 +354,10 @@ def main():
     for i in range(args.steps):
         flush_l2()
         step_device(args.warmup + i, reg_p)
-        st = reg_p.last_stats
-        k_ms += st.kernel_ms
-        k_launch += st.kernel_launches
-        k_bytes += st.algo_bytes
+        st = reg_p.last_batch_stats
+        k_ms += st[0].kernel_ms
+        k_launch += st[0].kernel_launches
+        k_bytes += sum(x.algo_bytes for x in st)
     peak, peak_src = load_peaks()
     achieved = (k_bytes / max(k_launch, 1)) / ((k_ms / max(k_launch, 1)) * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
@@ -363,9 +368,21 @@ def main():
         except Exception:
             traffic = None
 
-    total_scans = args.steps * world_size
+    total_scans = args.steps * world_size * B
     value = total_scans / (ms_dev * 1e-3)
     e2e = total_scans / (ms_e2e * 1e-3)
+
+    # latency figure beside the throughput: one scan per call (the reference's Match signature), L2 flushed, device-resident scan
+    lat_ms = 0.0
+    n_lat = min(args.steps, 10)
+    for i in range(n_lat + 2):
+        flush_l2()
+        T = guesses[i % n_scans].copy()
+        ds = d_scans[i % n_scans]
+        reg.match_device(ds.data_ptr(), ds.shape[0], T)
+        if i >= 2:
+            lat_ms += reg.last_stats.gpu_ms
+    single = {"ms_per_match_gpu_span": lat_ms / max(n_lat, 1), "scans_per_s": 1e3 * n_lat / max(lat_ms, 1e-9)}
 
     cpu = None
     if rank == 0 and world_size == 1:
@@ -396,17 +413,18 @@ def main():
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": args.workload, "desc": wl["desc"], "map_points": int(mi.n_points), "map_voxels": int(mi.n_voxels),
-                       "scan_points": int(np.mean([len(s) for s in scans])), "scans_per_gpu_per_step": 1, "gn_iter_cap": int(cfg.max_iterations),
-                       "mean_gn_iters": iters / max(args.steps, 1), "parallelism": f"scan-sharded x{world_size}, map replicated",
+                       "scan_points": int(np.mean([len(s) for s in scans])), "scans_per_gpu_per_step": B, "gn_iter_cap": int(cfg.max_iterations),
+                       "mean_gn_iters": iters / max(args.steps * B, 1), "parallelism": f"scan-sharded x{world_size}, map replicated",
                        "l2": "flushed between timed steps (256 MiB write), per-step CUDA events summed",
                        "median_pos_err_vs_truth_m": pos},
             "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d // max(args.steps, 1), "d2h_bytes_per_step": d2h // max(args.steps, 1),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "p2plane_gn_kernel (whole GN loop fused: iVox 5-NN + plane fit + J/r + 6x6 reduction + solve; "
-                                   "one launch = every iteration of one Match)", "achieved": achieved,
+                                   "one launch = every iteration of every scan of the batch)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "launches": int(k_launch), "avg_launch_us": 1e3 * k_ms / max(k_launch, 1), "algo_bytes_per_launch": k_bytes / max(k_launch, 1)},
+            "single_scan_latency": single,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "other_kernels": other,

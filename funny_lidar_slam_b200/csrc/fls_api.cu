@@ -179,16 +179,16 @@ int Handle::add_cloud_ivox(const void* pts, size_t n, size_t stride) {
 int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* n, double* T, int* converged, fls_match_stats* st) {
     if (ivox.n_pts == 0) return FLS_ERR_NO_MAP;
     if (B < 1 || B > kMaxBatch) return FLS_ERR_INVALID_ARG;
-    int off[kMaxBatch + 1], grid_of[kMaxBatch], cta_begin[kMaxBatch + 1];
+    int off[kMaxBatch + 1];
     off[0] = 0;
-    cta_begin[0] = 0;
+    int grid = 1;
     for (int s = 0; s < B; ++s) {
         if (n[s] > 0x3fffffffull || (long long)off[s] + (long long)n[s] > 0x7ffffff0ll) return FLS_ERR_INVALID_ARG;
         off[s + 1] = off[s] + (int)n[s];
-        grid_of[s] = p2plane_grid((int)n[s], cfg.device, B);
-        cta_begin[s + 1] = cta_begin[s] + grid_of[s];
+        const int g = p2plane_grid((int)n[s], cfg.device);
+        if (g > grid) grid = g;
     }
-    const int n_total = off[B], grid = cta_begin[B];
+    const int n_total = off[B];
     const size_t nt = (size_t)n_total;
     rec0.reserve(nt + 1);
     rec1.reserve(nt + 1);
@@ -200,15 +200,15 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
     // is ever cleared — only zeroed when (re)allocated, so that uninitialised memory cannot alias a tag
     {
         const size_t cap0 = ll_rows.cap;
-        ll_rows.reserve((size_t)grid * 32 + (size_t)B * kLlPoseLen);
+        ll_rows.reserve((size_t)B * grid * 32 + (size_t)B * kLlPoseLen);
         if (ll_rows.cap != cap0) FLS_CUDA(cudaMemsetAsync(ll_rows.p, 0, ll_rows.cap * sizeof(uint4), stream));
     }
     match_epoch = (match_epoch + 1) & 0xffffffu;
     if (match_epoch == 0) match_epoch = 1;
     // ---- per-batch tables, staged in one pinned block and sent with one copy -------------------------------------------
     const size_t o_pose = 0, o_off = o_pose + sizeof(PoseArg) * kMaxBatch, o_desc = o_off + sizeof(int) * (kMaxBatch + 4),
-                 o_ptr = o_desc + sizeof(P2PlaneScan) * kMaxBatch, o_cta = o_ptr + sizeof(void*) * kMaxBatch;
-    const size_t tbl_bytes = o_cta + sizeof(int) * (size_t)(grid + 4);
+                 o_ptr = o_desc + sizeof(P2PlaneScan) * kMaxBatch;
+    const size_t tbl_bytes = o_ptr + sizeof(void*) * kMaxBatch;
     if (tbl_bytes > h_batch_cap) {
         if (h_batch) cudaFreeHost(h_batch);
         h_batch = nullptr;
@@ -221,8 +221,7 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
     int* ho = reinterpret_cast<int*>(h_batch + o_off);
     P2PlaneScan* hd = reinterpret_cast<P2PlaneScan*>(h_batch + o_desc);
     const float4** hq = reinterpret_cast<const float4**>(h_batch + o_ptr);
-    int* hc = reinterpret_cast<int*>(h_batch + o_cta);
-    uint4* pose_base = ll_rows.p + (size_t)grid * 32;
+    uint4* pose_base = ll_rows.p + (size_t)B * grid * 32;
     for (int s = 0; s < B; ++s) {
         const double* Ts = T + 16 * s;
         for (int r = 0; r < 3; ++r) {
@@ -234,17 +233,14 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
         P2PlaneScan& d = hd[s];
         d.src = src_f.p + off[s];
         d.n = (int)n[s];
-        d.cta_begin = cta_begin[s];
-        d.cta_count = grid_of[s];
         d.tag_base = match_epoch << 8;
         d.state = state.p + s;
         d.rec0 = rec0.p + off[s];
         d.rec1 = rec1.p + off[s];
         d.flags = flags.p + off[s];
-        d.rows = ll_rows.p + (size_t)cta_begin[s] * 32;
+        d.rows = ll_rows.p + (size_t)s * grid * 32;
         d.ll_pose = pose_base + (size_t)s * kLlPoseLen;
         d.log = log_cap ? log.p + (size_t)s * log_cap : nullptr;
-        for (int k = 0; k < grid_of[s]; ++k) hc[cta_begin[s] + k] = s;
     }
     ho[B] = off[B];
     FLS_CUDA(cudaMemcpyAsync(d_batch.p, h_batch, tbl_bytes, cudaMemcpyHostToDevice, stream));
@@ -253,7 +249,6 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
     const int* d_off = reinterpret_cast<const int*>(d_batch.p + o_off);
     const P2PlaneScan* d_desc = reinterpret_cast<const P2PlaneScan*>(d_batch.p + o_desc);
     const float4* const* d_ptrs = reinterpret_cast<const float4* const*>(d_batch.p + o_ptr);
-    const int* d_cta = reinterpret_cast<const int*>(d_batch.p + o_cta);
     // one prep kernel (state init, flag reset, locality keys) + ONE radix sort + gather for the whole batch: the queries of
     // every scan end up in Morton order of the voxel they fall into at the initial pose (locality only: the sums are
     // order-free up to fp64 rounding, and the persistent per-point records live in the same order for the whole Match)
@@ -269,7 +264,7 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
     a.gp.pos_thres = cfg.position_converge_thres;
     a.log_cap = log_cap;
     a.scans = d_desc;
-    a.cta_scan = d_cta;
+    a.n_scans = B;
     // roofline accounting (SURVEY.md §8d, K1 — the REFERENCE algorithm's traffic): 16 B source point + n_stencil x 16 B
     // slot probes + 32 B persistent record per point-iteration, 16 B per map record resident in the stencil voxels.
     per_point_iter_bytes = 16 + 16LL * a.map.n_stencil + 32;

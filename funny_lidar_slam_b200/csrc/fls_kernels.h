@@ -23,13 +23,12 @@ struct PoseArg {
 struct P2PlaneScan {
     const float4* src;  // body-frame scan in Morton order of the query voxel, packed float4
     int n;
-    int cta_begin, cta_count;  // this scan's CTAs: [cta_begin, cta_begin + cta_count); the first one folds and solves
     unsigned tag_base;         // Match epoch << 8 (hand-over tags, fls_gn.cuh)
     GnState* state;
     float4* rec0;  // persistent per-point record: J0..J3
     float4* rec1;  //                              J4, J5, |d|, 1
     unsigned char* flags;
-    uint4* rows;     // [cta_count][32] LL records {lo, tag, hi, tag}: one per CTA and sum
+    uint4* rows;     // [grid][32] LL records {lo, tag, hi, tag}: one per CTA and sum
     uint4* ll_pose;  // [kLlPoseLen] LL records: next pose + stop word, published by the folding CTA
     fls_iter_log* log;
 };
@@ -40,13 +39,13 @@ struct P2PlaneLoopArgs {
     double plane_thres;
     GnParams gp;
     int log_cap;
-    const P2PlaneScan* scans;  // [n_scans]
-    const int* cta_scan;       // [grid] scan index of every CTA
+    const P2PlaneScan* scans;  // [n_scans]; every CTA serves every scan, CTA (s mod grid) folds and solves scan s
+    int n_scans;
 };
 int p2plane_block();                   // threads per CTA of the selected kernel shape
 int p2plane_max_grid(int device);      // co-resident CTAs
 int p2plane_chunks(int n);             // warp-sized (32-point) work chunks
-int p2plane_grid(int n, int device, int share = 1);  // CTAs for one scan when `share` scans split the device
+int p2plane_grid(int n, int device);    // CTAs that serve a scan of n points: its chunks / warps per CTA, + the folder, <= co-resident
 void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st);
 // d_scan_ptrs[n_scans]: device pointers of the scans; d_offsets[n_scans + 1]: their positions in the batch; d_poses / d_states[n_scans]
 void prepare_queries(const float4* const* d_scan_ptrs, int n_total, const int* d_offsets, int n_scans, const PoseArg* d_poses, GnState* d_states,

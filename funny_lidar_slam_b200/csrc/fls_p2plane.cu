@@ -212,18 +212,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
     extern __shared__ __align__(16) unsigned char s_dyn[];
     double (*s_rec)[32][kRecW] = reinterpret_cast<double (*)[32][kRecW]>(s_dyn);  // [W][32][kRecW] per-lane staging records
     __shared__ double s_red[W][32];
-    __shared__ int s_done;
+    __shared__ int s_stop;
+    __shared__ unsigned char s_iter[kMaxBatch];  // iterations this CTA has completed of every scan (255 = scan finished)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // One launch serves a batch of independent scans: this CTA belongs to scan `sc` and is CTA `cta` of its `G`.  Every
-    // scan runs its own Gauss-Newton loop with its own hand-over records; scans never synchronise with each other, so
-    // while one scan's CTAs wait for their solve the SM keeps working on the CTAs of another.
-    const P2PlaneScan sc = a.scans[a.cta_scan[blockIdx.x]];
-    const int cta = (int)blockIdx.x - sc.cta_begin, G = sc.cta_count;
-    const int n_chunks = (sc.n + 31) >> 5;  // warp-sized chunks
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
     const int n_warps = G * W;
-    // CTA 0 of the scan folds and solves; chunks are dealt from the highest CTA index down so that CTA 0 is the one that
-    // stays idle whenever the scan has more warps than chunks (p2plane_grid adds one CTA for that purpose)
-    const int first_chunk = (G - 1 - cta) * W + warp;
 
     // which product of record columns lane k accumulates: sum_k = sgn * sum_p rec[p][ca] * rec[p][cb]
     int ca = kRecOne, cb = kRecOne;
@@ -246,135 +239,172 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
     } else {
         sgn = 0.0;
     }
-
-    if (threadIdx.x < 9) s_pose[threadIdx.x] = __ldcg(&sc.state->R[threadIdx.x]);
-    else if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(&sc.state->t[threadIdx.x - 9]);
+    if (threadIdx.x < kMaxBatch) s_iter[threadIdx.x] = 0;
     __syncthreads();
 
-    for (int it = 0; it < a.gp.max_iterations; ++it) {
-        const unsigned tag = sc.tag_base | (unsigned)(it + 1);
-        if (cta == 0 && threadIdx.x == 0 && it < 16) sc.state->dbg[it][0] = globaltimer_ns();
-
-        double acc = 0.0;  // lane k's running sum over every chunk of this warp
-        // warp-granular work loop, static round-robin over 32-point chunks: no barrier, no atomics inside
-        // (consecutive chunks stay in one CTA: Morton neighbours share candidate lists in L1 — spreading them over SMs
-        //  for balance was measured 35 % slower)
-        for (int chunk = first_chunk; chunk < n_chunks; chunk += n_warps) {
-            const int i = (chunk << 5) + lane;
-            double J[6] = {0, 0, 0, 0, 0, 0}, ad = 0.0, vflag = 0.0;
-            unsigned n_cand = 0, n_fb = 0;
-            if (i < sc.n) {
-                const float4 sp = sc.src[i];
-                bool use = p2plane_point(a.map, sp, s_pose, a.plane_thres, J, ad, n_cand, n_fb);
-                if (use) {
-                    sc.rec0[i] = make_float4((float)J[0], (float)J[1], (float)J[2], (float)J[3]);
-                    sc.rec1[i] = make_float4((float)J[4], (float)J[5], (float)ad, 1.0f);
-                    sc.flags[i] = 1;
-                } else if (sc.flags[i]) {  // stale contribution [quirk 1]
-                    const float4 r0 = sc.rec0[i], r1 = sc.rec1[i];
-                    J[0] = r0.x; J[1] = r0.y; J[2] = r0.z; J[3] = r0.w; J[4] = r1.x; J[5] = r1.y;
-                    ad = r1.z;
-                    use = true;
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) J[k] = 0.0;
-                    ad = 0.0;
-                }
-                vflag = use ? 1.0 : 0.0;
+    // One launch serves a batch of independent scans and EVERY CTA works on EVERY scan: the grid sweeps the scans round-
+    // robin, one Gauss-Newton iteration of one scan per visit.  A visit ends with this CTA's row of partial sums going out
+    // as LL records; only the scan's folding CTA waits for the other rows, solves and publishes the next pose — everybody
+    // else moves straight on to the next scan, and by the time the sweep returns to this scan its pose has long been
+    // published.  The hand-over latency of one scan is hidden behind the work on the others; finished scans drop out of
+    // the sweep, so the remaining ones simply come round faster (no static partition of the SMs, no idle CTAs).
+    // With a single scan the sweep degenerates to: work, publish, wait for the pose.
+    int n_left = a.n_scans;
+    while (n_left > 0) {
+        for (int s = 0; s < a.n_scans; ++s) {
+            const int it = s_iter[s];
+            if (it == 255) continue;
+            const P2PlaneScan* __restrict__ sc = a.scans + s;
+            GnState* const state = sc->state;
+            // ---- pose of this iteration: the prep kernel's state for iteration 0, afterwards the LL record published by
+            // the scan's folder at the end of iteration it-1 (12 values + the stop word)
+            if (it == 0) {
+                if (threadIdx.x < 9) s_pose[threadIdx.x] = __ldcg(&state->R[threadIdx.x]);
+                else if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(&state->t[threadIdx.x - 9]);
+                if (threadIdx.x == 12) s_stop = 0;
+            } else if (threadIdx.x < 13) {
+                const unsigned ptag = sc->tag_base | (unsigned)it;
+                const uint4* ll = sc->ll_pose;
+                double v;
+                while (!ll_load(ll + threadIdx.x, ptag, v)) __nanosleep(100);
+                if (threadIdx.x < 12) s_pose[threadIdx.x] = v;
+                else s_stop = v != 0.0;
             }
-            double* rec = s_rec[warp][lane];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) rec[k] = J[k];
-            rec[kRecAd] = ad;
-            rec[kRecValid] = vflag;
-            rec[kRecCand] = (double)n_cand;
-            rec[kRecHits] = (double)n_fb;  // points that took the QR path (diagnostic; reported as hits_total)
-            rec[kRecOne] = 1.0;
-            __syncwarp();
-#pragma unroll 8
-            for (int p = 0; p < 32; ++p) acc += s_rec[warp][p][ca] * s_rec[warp][p][cb];
-            __syncwarp();
-        }
-        // ---- CTA row: one LL record per sum, no fence, no atomic ----------------------------------------------------------
-        s_red[warp][lane] = acc * sgn;
-        __syncthreads();
-        if (warp == 0) {
-            double v = 0;
-#pragma unroll
-            for (int w = 0; w < W; ++w) v += s_red[w][lane];
-            ll_store(sc.rows + (size_t)cta * 32 + lane, v, tag);
-        }
-        if (cta == 0) {
-            // ---- fold: warp w owns rows w, w+W, ...; every sweep re-reads all of them (independent loads, one L2 round
-            // trip) until each carries this iteration's tag, then the sums are taken in a fixed order — bitwise
-            // reproducible, and the fold is finished one sweep after the slowest CTA's row lands
-            GnPre pre;
-            if (threadIdx.x == 0) gn_load(sc.state, pre);  // off the critical path: the state is stable until gn_step below
-            __syncthreads();  // s_red is free again
-            const int nrows = G;
-            double sum;
-            for (;;) {
-                bool ok = true;
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                int r = warp;
-                for (; r + 7 * W < nrows; r += 8 * W) {  // 8 independent 16-byte loads in flight per lane
-                    double v0, v1, v2, v3, v4, v5, v6, v7;
-                    const bool k0 = ll_load(sc.rows + (size_t)r * 32 + lane, tag, v0);
-                    const bool k1 = ll_load(sc.rows + (size_t)(r + W) * 32 + lane, tag, v1);
-                    const bool k2 = ll_load(sc.rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
-                    const bool k3 = ll_load(sc.rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
-                    const bool k4 = ll_load(sc.rows + (size_t)(r + 4 * W) * 32 + lane, tag, v4);
-                    const bool k5 = ll_load(sc.rows + (size_t)(r + 5 * W) * 32 + lane, tag, v5);
-                    const bool k6 = ll_load(sc.rows + (size_t)(r + 6 * W) * 32 + lane, tag, v6);
-                    const bool k7 = ll_load(sc.rows + (size_t)(r + 7 * W) * 32 + lane, tag, v7);
-                    ok = ok && k0 && k1 && k2 && k3 && k4 && k5 && k6 && k7;
-                    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
-                    a0 += v4; a1 += v5; a2 += v6; a3 += v7;
-                }
-                for (; r + 3 * W < nrows; r += 4 * W) {
-                    double v0, v1, v2, v3;
-                    const bool k0 = ll_load(sc.rows + (size_t)r * 32 + lane, tag, v0);
-                    const bool k1 = ll_load(sc.rows + (size_t)(r + W) * 32 + lane, tag, v1);
-                    const bool k2 = ll_load(sc.rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
-                    const bool k3 = ll_load(sc.rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
-                    ok = ok && k0 && k1 && k2 && k3;
-                    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
-                }
-                for (; r < nrows; r += W) {
-                    double v0;
-                    ok = ok && ll_load(sc.rows + (size_t)r * 32 + lane, tag, v0);
-                    a0 += v0;
-                }
-                sum = (a0 + a1) + (a2 + a3);
-                if (__all_sync(0xffffffffu, ok)) break;
-                __nanosleep(100);
-            }
-            s_red[warp][lane] = sum;
             __syncthreads();
-            if (warp == 0) {
-                if (lane == 0 && it < 16) sc.state->dbg[it][1] = globaltimer_ns();
-                double t = 0;
+            if (s_stop) {  // uniform: the scan finished with iteration it-1
+                if (threadIdx.x == 0) s_iter[s] = 255;
+                __syncthreads();  // everybody has read s_stop; s_iter is visible before the next sweep
+                --n_left;
+                continue;
+            }
+            const unsigned tag = sc->tag_base | (unsigned)(it + 1);
+            const int folder = s % G;
+            if (cta == folder && threadIdx.x == 0 && it < 16) state->dbg[it][0] = globaltimer_ns();
+            const int n = sc->n;
+            const int n_chunks = (n + 31) >> 5;  // warp-sized chunks
+            const float4* __restrict__ src = sc->src;
+            float4* __restrict__ rec0 = sc->rec0;
+            float4* __restrict__ rec1 = sc->rec1;
+            unsigned char* __restrict__ flags = sc->flags;
+            // the folder takes the last block of chunks: it is the CTA that stays idle when the scan has fewer chunks than
+            // the grid has warps (p2plane_grid adds one CTA for that purpose)
+            const int slot = (cta - folder - 1 + G) % G;
+
+            double acc = 0.0;  // lane k's running sum over every chunk of this warp
+            // warp-granular work loop, static round-robin over 32-point chunks: no barrier, no atomics inside
+            // (consecutive chunks stay in one CTA: Morton neighbours share candidate lists in L1 — spreading them over SMs
+            //  for balance was measured 35 % slower)
+            for (int chunk = slot * W + warp; chunk < n_chunks; chunk += n_warps) {
+                const int i = (chunk << 5) + lane;
+                double J[6] = {0, 0, 0, 0, 0, 0}, ad = 0.0, vflag = 0.0;
+                unsigned n_cand = 0, n_fb = 0;
+                if (i < n) {
+                    const float4 sp = src[i];
+                    bool use = p2plane_point(a.map, sp, s_pose, a.plane_thres, J, ad, n_cand, n_fb);
+                    if (use) {
+                        rec0[i] = make_float4((float)J[0], (float)J[1], (float)J[2], (float)J[3]);
+                        rec1[i] = make_float4((float)J[4], (float)J[5], (float)ad, 1.0f);
+                        flags[i] = 1;
+                    } else if (flags[i]) {  // stale contribution [quirk 1]
+                        const float4 r0 = rec0[i], r1 = rec1[i];
+                        J[0] = r0.x; J[1] = r0.y; J[2] = r0.z; J[3] = r0.w; J[4] = r1.x; J[5] = r1.y;
+                        ad = r1.z;
+                        use = true;
+                    } else {
 #pragma unroll
-                for (int w = 0; w < W; ++w) t += s_red[w][lane];
+                        for (int k = 0; k < 6; ++k) J[k] = 0.0;
+                        ad = 0.0;
+                    }
+                    vflag = use ? 1.0 : 0.0;
+                }
+                double* rec = s_rec[warp][lane];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) rec[k] = J[k];
+                rec[kRecAd] = ad;
+                rec[kRecValid] = vflag;
+                rec[kRecCand] = (double)n_cand;
+                rec[kRecHits] = (double)n_fb;  // points that took the QR path (diagnostic; reported as hits_total)
+                rec[kRecOne] = 1.0;
                 __syncwarp();
-                s_red[0][lane] = t;
+#pragma unroll 8
+                for (int p = 0; p < 32; ++p) acc += s_rec[warp][p][ca] * s_rec[warp][p][cb];
                 __syncwarp();
-                if (lane == 0) {
-                    if (it < 16) sc.state->dbg[it][2] = globaltimer_ns();
-                    gn_step_pre(sc.state, pre, s_red[0], a.gp, sc.log, a.log_cap, nullptr, 0, sc.ll_pose, tag);
-                    if (it < 16) sc.state->dbg[it][3] = globaltimer_ns();
+            }
+            // ---- CTA row: one LL record per sum, no fence, no atomic ------------------------------------------------------
+            s_red[warp][lane] = acc * sgn;
+            __syncthreads();
+            uint4* const rows = sc->rows;
+            if (warp == 0) {
+                double v = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) v += s_red[w][lane];
+                ll_store(rows + (size_t)cta * 32 + lane, v, tag);
+            }
+            if (cta == folder) {
+                // ---- fold: warp w owns rows w, w+W, ...; every sweep re-reads all of them (independent loads, one L2 round
+                // trip) until each carries this iteration's tag, then the sums are taken in a fixed order — bitwise
+                // reproducible, and the fold is finished one sweep after the slowest CTA's row lands
+                GnPre pre;
+                if (threadIdx.x == 0) gn_load(state, pre);  // off the critical path: the state is stable until gn_step below
+                __syncthreads();  // s_red is free again
+                const int nrows = G;
+                double sum;
+                for (;;) {
+                    bool ok = true;
+                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                    int r = warp;
+                    for (; r + 7 * W < nrows; r += 8 * W) {  // 8 independent 16-byte loads in flight per lane
+                        double v0, v1, v2, v3, v4, v5, v6, v7;
+                        const bool k0 = ll_load(rows + (size_t)r * 32 + lane, tag, v0);
+                        const bool k1 = ll_load(rows + (size_t)(r + W) * 32 + lane, tag, v1);
+                        const bool k2 = ll_load(rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
+                        const bool k3 = ll_load(rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
+                        const bool k4 = ll_load(rows + (size_t)(r + 4 * W) * 32 + lane, tag, v4);
+                        const bool k5 = ll_load(rows + (size_t)(r + 5 * W) * 32 + lane, tag, v5);
+                        const bool k6 = ll_load(rows + (size_t)(r + 6 * W) * 32 + lane, tag, v6);
+                        const bool k7 = ll_load(rows + (size_t)(r + 7 * W) * 32 + lane, tag, v7);
+                        ok = ok && k0 && k1 && k2 && k3 && k4 && k5 && k6 && k7;
+                        a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+                        a0 += v4; a1 += v5; a2 += v6; a3 += v7;
+                    }
+                    for (; r + 3 * W < nrows; r += 4 * W) {
+                        double v0, v1, v2, v3;
+                        const bool k0 = ll_load(rows + (size_t)r * 32 + lane, tag, v0);
+                        const bool k1 = ll_load(rows + (size_t)(r + W) * 32 + lane, tag, v1);
+                        const bool k2 = ll_load(rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
+                        const bool k3 = ll_load(rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
+                        ok = ok && k0 && k1 && k2 && k3;
+                        a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+                    }
+                    for (; r < nrows; r += W) {
+                        double v0;
+                        ok = ok && ll_load(rows + (size_t)r * 32 + lane, tag, v0);
+                        a0 += v0;
+                    }
+                    sum = (a0 + a1) + (a2 + a3);
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    __nanosleep(100);
+                }
+                s_red[warp][lane] = sum;
+                __syncthreads();
+                if (warp == 0) {
+                    if (lane == 0 && it < 16) state->dbg[it][1] = globaltimer_ns();
+                    double t = 0;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) t += s_red[w][lane];
+                    __syncwarp();
+                    s_red[0][lane] = t;
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (it < 16) state->dbg[it][2] = globaltimer_ns();
+                        gn_step_pre(state, pre, s_red[0], a.gp, sc->log, a.log_cap, nullptr, 0, sc->ll_pose, tag);
+                        if (it < 16) state->dbg[it][3] = globaltimer_ns();
+                    }
                 }
             }
+            if (threadIdx.x == 0) s_iter[s] = (unsigned char)(it + 1);
+            __syncthreads();  // s_red / s_pose / s_iter are reused by the next visit
         }
-        // ---- next pose: everybody polls the LL pose record (12 values + the stop word) -----------------------------------
-        if (threadIdx.x < 13) {
-            double v;
-            while (!ll_load(sc.ll_pose + threadIdx.x, tag, v)) __nanosleep(100);
-            if (threadIdx.x < 12) s_pose[threadIdx.x] = v;
-            else s_done = v != 0.0;
-        }
-        __syncthreads();
-        if (s_done) break;
     }
 }
 
@@ -594,11 +624,10 @@ int p2plane_max_grid(int device) {
 
 int p2plane_chunks(int n) { return (n + 31) / 32; }
 
-int p2plane_grid(int n, int device, int share) {
+int p2plane_grid(int n, int device) {
     const int W = p2plane_block() / 32;
     const int need = (p2plane_chunks(n) + W - 1) / W;
-    int cap = p2plane_max_grid(device) / (share > 0 ? share : 1);
-    if (cap < 1) cap = 1;
+    const int cap = p2plane_max_grid(device);
     const int g = need + 1 < cap ? need + 1 : cap;  // + the folding CTA (stays without chunks when there is room)
     return g > 0 ? g : 1;
 }
