@@ -138,6 +138,10 @@ def secondary_kernels(device: int, peak: float, log, steps: int = 6):
     dev = torch.device("cuda", device)
     for name, method, sensor, dpos, drot, extra in (
             ("ndt_64line", _abi.FLS_NDT, "hdl64", 0.05, 0.5, dict(ndt_capacity=2000000)),
+            # BASELINE config 5: dense 128-line scan (~260 k pts), no down-sampling (a 1 cm leaf makes pcl::VoxelGrid return its
+            # input: dx*dy*dz > INT_MAX), exactly 10 GN iterations (thresholds 0)
+            ("ndt_128line_10iters", _abi.FLS_NDT, "os128", 0.05, 0.5,
+             dict(ndt_capacity=2000000, source_cloud_filter_size=0.01, max_iterations=10, position_converge_thres=0.0, rotation_converge_thres=0.0)),
             ("icp_16line", _abi.FLS_ICP_P2P, "vlp16", 0.3, 3.0, {})):
         scans = [synth.make_scan(world, traj[3 + 2 * i], sensor, seed=300 + i)["points"] for i in range(3)]
         guesses = [synth.perturb_pose(traj[3 + 2 * i], seed=900 + i, dpos=dpos, drot_deg=drot) for i in range(3)]

@@ -585,13 +585,23 @@ __global__ void ivox_insert_scatter_kernel(const unsigned char* __restrict__ cls
     else if (c == 2) out[n1 + (unsigned)(excl[i] >> 32)] = world[i];
 }
 
-// Two shapes of the same kernel: 2 x 384 threads per SM (<= 80 registers) or 1 x 768 — the same 24 resident warps, half
-// the CTA rows to fold.  FLS_P2PLANE_BLOCK=384|768 overrides the default.
+// Shapes of the same kernel: BLOCK threads x kMinB CTAs per SM = the same 24 resident warps (<= 80 registers).  Small CTAs
+// mean small barrier groups (a visit ends with one __syncthreads: every warp waits for the slowest of its CTA) but more
+// rows to fold; with a batch the fold is hidden behind the other scans.  FLS_P2PLANE_BLOCK=96|192|384|768 overrides.
 template <int BLOCK>
 struct P2PlaneShape {
-    static constexpr int kMinB = BLOCK == 384 ? 2 : 1;
+    static constexpr int kMinB = 768 / BLOCK;
     static const void* fn() { return (const void*)p2plane_gn_kernel<BLOCK, kMinB>; }
     static size_t smem() { return (size_t)(BLOCK / 32) * 32 * kRecW * sizeof(double); }
+    static int max_grid(int sms) {
+        int per_sm = 0;
+        cudaFuncSetAttribute(fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2plane_gn_kernel<BLOCK, kMinB>, BLOCK, smem());
+        return sms * (per_sm > 0 ? per_sm : 1);
+    }
+    static void launch(int grid, void** params, cudaStream_t st) {
+        FLS_CUDA(cudaLaunchCooperativeKernel(fn(), dim3(grid), dim3(BLOCK), params, smem(), st));
+    }
 };
 
 }  // namespace
@@ -600,7 +610,8 @@ int p2plane_block() {
     static int block = 0;
     if (!block) {
         const char* e = std::getenv("FLS_P2PLANE_BLOCK");
-        block = (e && std::atoi(e) == 384) ? 384 : ((e && std::atoi(e) == 768) ? 768 : kP2PlaneBlock);
+        const int v = e ? std::atoi(e) : 0;
+        block = (v == 96 || v == 192 || v == 384 || v == 768) ? v : kP2PlaneBlock;
     }
     return block;
 }
@@ -608,16 +619,15 @@ int p2plane_block() {
 int p2plane_max_grid(int device) {
     static int cached[64] = {0};
     if (device >= 0 && device < 64 && cached[device]) return cached[device];
-    int sms = 0, per_sm = 0;
+    int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (p2plane_block() == 384) {
-        cudaFuncSetAttribute(P2PlaneShape<384>::fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2PlaneShape<384>::smem());
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2plane_gn_kernel<384, 2>, 384, P2PlaneShape<384>::smem());
-    } else {
-        cudaFuncSetAttribute(P2PlaneShape<768>::fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2PlaneShape<768>::smem());
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2plane_gn_kernel<768, 1>, 768, P2PlaneShape<768>::smem());
+    int g;
+    switch (p2plane_block()) {
+        case 96: g = P2PlaneShape<96>::max_grid(sms); break;
+        case 192: g = P2PlaneShape<192>::max_grid(sms); break;
+        case 384: g = P2PlaneShape<384>::max_grid(sms); break;
+        default: g = P2PlaneShape<768>::max_grid(sms); break;
     }
-    const int g = sms * (per_sm > 0 ? per_sm : 1);
     if (device >= 0 && device < 64) cached[device] = g;
     return g;
 }
@@ -635,10 +645,12 @@ int p2plane_grid(int n, int device) {
 void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st) {
     P2PlaneLoopArgs args = a;
     void* params[] = {&args};
-    if (p2plane_block() == 384)
-        FLS_CUDA(cudaLaunchCooperativeKernel(P2PlaneShape<384>::fn(), dim3(grid), dim3(384), params, P2PlaneShape<384>::smem(), st));
-    else
-        FLS_CUDA(cudaLaunchCooperativeKernel(P2PlaneShape<768>::fn(), dim3(grid), dim3(768), params, P2PlaneShape<768>::smem(), st));
+    switch (p2plane_block()) {
+        case 96: P2PlaneShape<96>::launch(grid, params, st); break;
+        case 192: P2PlaneShape<192>::launch(grid, params, st); break;
+        case 384: P2PlaneShape<384>::launch(grid, params, st); break;
+        default: P2PlaneShape<768>::launch(grid, params, st); break;
+    }
 }
 
 // Per-batch preparation: state init + flag reset + locality keys (one kernel), then order every scan by the voxel each
