@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from funny_lidar_slam_b200 import FLS_ICP_P2P, FLS_NDT, FLS_P2PLANE_IVOX, default_config, synth  # noqa: E402
-from funny_lidar_slam_b200._abi import FLS_FLAG_ITER_LOG  # noqa: E402
+from funny_lidar_slam_b200._abi import FLS_FLAG_ITER_LOG, FLS_LOAM_FULL, FLS_P2PLANE_KNN  # noqa: E402
 from oracle import pyoracle as orc  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -51,6 +51,36 @@ def main():
              depth_checksum=float(np.sum(proj["depth"].astype(np.float64))))
     vg = orc.voxel_grid(sc["scan"], 0.4)
     np.savez(os.path.join(OUT, "voxelgrid_scene16_0p4.npz"), n=len(vg), checksum=float(np.sum(vg.astype(np.float64))), first=vg[:8], last=vg[-8:])
+    # kd-tree LOAM plug-ins on feature clouds (same scene as tests/test_oracle_loam_kd.py::feature_scene)
+    def feats(pose, seed):
+        pr = synth.make_projected_scan(sc["world"], pose, kind="spin", sensor="vlp16", seed=seed)
+        c_i, p_i, _ = orc.extract_features(pr["depth"], pr["col"], len(pr["ordered"]), pr["row_start"], pr["row_end"], 1.0, 0.1)
+        return pr["ordered"][p_i].copy(), pr["ordered"][c_i].copy()
+
+    def to_world(pts, T):
+        o = pts.copy()
+        o[:, :3] = (pts[:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+        return o
+
+    traj = sc["traj"]
+    maps = [feats(traj[k], k) for k in (3, 4, 6, 7)]
+    maps_p = [to_world(m[0], traj[k]) for m, k in zip(maps, (3, 4, 6, 7))]
+    maps_c = [to_world(m[1], traj[k]) for m, k in zip(maps, (3, 4, 6, 7))]
+    p5, c5 = feats(traj[5], 55)
+    guess = synth.perturb_pose(traj[5], dpos=0.1, drot_deg=1.0)
+
+    def pack(r, ok, T, st):
+        lg = r.iter_log()
+        return dict(T=T, ok=ok, iters=st.iterations, n_valid=st.n_valid, H0=lg[0]["H"], g0=lg[0]["g"],
+                    planar_checksum=float(np.sum(p5.astype(np.float64))))
+
+    r = orc.Registration(default_config(FLS_P2PLANE_KNN, flags=FLS_FLAG_ITER_LOG))
+    r.add_cloud(np.concatenate(maps_p))
+    np.savez(os.path.join(OUT, "kdtree_features.npz"), **pack(r, *r.match(p5, guess)))
+    r = orc.Registration(default_config(FLS_LOAM_FULL, localization_mode=0, flags=FLS_FLAG_ITER_LOG))
+    for mp_, mc_ in zip(maps_p, maps_c):
+        r.add_cloud(mp_, mc_)
+    np.savez(os.path.join(OUT, "loamfull_features.npz"), **pack(r, *r.match(p5, guess, corner=c5)))
     print("golden vectors written to", OUT)
 
 
