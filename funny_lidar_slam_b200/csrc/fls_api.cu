@@ -143,14 +143,17 @@ void Handle::set_fit_cloud(const float4* d, size_t n) {
 
 // ---- control block of a persistent GN loop (K2 / K3): rows + hand-over counters + stop rule ------------------------
 static GnLoopCtl make_ctl(Handle& h, int method, int grid, int min_effective) {
-    const size_t n_sync = 2 * (size_t)h.cfg.max_iterations + 2;
-    h.sync_buf.reserve(n_sync);
-    h.partials.reserve((size_t)(grid + 1) * 32);
+    // LL hand-over records (fls_gn.cuh): never cleared, tags are unique per Match and iteration; zeroed only when (re)allocated
+    const size_t cap0 = h.ll_rows.cap;
+    h.ll_rows.reserve((size_t)grid * 32 + kLlPoseLen);
+    if (h.ll_rows.cap != cap0) FLS_CUDA(cudaMemsetAsync(h.ll_rows.p, 0, h.ll_rows.cap * sizeof(uint4), h.stream));
+    h.match_epoch = (h.match_epoch + 1) & 0xffffffu;
+    if (h.match_epoch == 0) h.match_epoch = 1;
     GnLoopCtl c;
     c.state = h.state.p;
-    c.rows = h.partials.p;
-    c.sync = h.sync_buf.p;
-    c.sync_flag = h.sync_buf.p + 2 * (size_t)h.cfg.max_iterations;
+    c.ll_rows = h.ll_rows.p;
+    c.ll_pose = h.ll_rows.p + (size_t)grid * 32;
+    c.tag_base = h.match_epoch << 8;
     c.gp.method = method;
     c.gp.max_iterations = h.cfg.max_iterations;
     c.gp.min_effective = min_effective;
@@ -378,7 +381,7 @@ int Handle::match_ndt(const float4* d_in, size_t n_in, double* T, int* converged
     GnLoopCtl ctl = make_ctl(*this, FLS_NDT, grid, cfg.ndt_min_effective_pts);
     double T_in[16];
     std::memcpy(T_in, T, sizeof(T_in));
-    launch_gn_init(state.p, T, stream, sync_buf.p, 2 * cfg.max_iterations + 2);
+    launch_gn_init(state.p, T, stream);
     launches++;
     NdtArgs a;
     a.src = src_f.p;
@@ -491,7 +494,7 @@ int Handle::match_icp(const float4* d_in, size_t n_in, double* T, int* converged
     const int ni = (int)n;
     const int grid = icp_grid_blocks(ni, cfg.device);
     GnLoopCtl ctl = make_ctl(*this, FLS_ICP_P2P, grid, 0);
-    launch_gn_init(state.p, T, stream, sync_buf.p, 2 * cfg.max_iterations + 2);
+    launch_gn_init(state.p, T, stream);
     launches++;
     IcpArgs a;
     a.src = src_f.p;
@@ -603,7 +606,7 @@ int Handle::match_kd(const float4* d_planar, size_t n_planar, const float4* d_co
     const int ni = (int)n;
     const int grid = loam_grid_blocks(ni, cfg.device);
     GnLoopCtl ctl = make_ctl(*this, cfg.method, grid, 50);
-    launch_gn_init(state.p, T, stream, sync_buf.p, 2 * cfg.max_iterations + 2);
+    launch_gn_init(state.p, T, stream);
     launches++;
     rec_d.reserve(n * 8 + 8);
     flags.reserve(n + 1);
@@ -847,12 +850,12 @@ static int validate(const fls_config* c) {
     if (c->method < 0 || c->method > FLS_LOAM_FULL) return FLS_ERR_INVALID_ARG;
     // the reference CHECK_NE()s every threshold against its "NaN" sentinel = numeric_limits::max (constant_variable.h:10-15)
     if (c->max_iterations <= 0 || c->max_iterations == 2147483647) return FLS_ERR_INVALID_ARG;
+    if (c->max_iterations > 254) return FLS_ERR_UNSUPPORTED;  // 8-bit iteration field of the hand-over tags (fls_gn.cuh); upstream configs use 8-30
     if (!(c->position_converge_thres < 1e300) || !(c->rotation_converge_thres < 1e300)) return FLS_ERR_INVALID_ARG;
     if (c->ivox_nearby < 0 || c->ivox_nearby > 3) return FLS_ERR_INVALID_ARG;
     if (c->method == FLS_P2PLANE_IVOX) {
         if (!(c->point_to_planar_thres < 1e300) || !(c->ivox_resolution > 0.f)) return FLS_ERR_INVALID_ARG;
         if (c->ivox_k != 5) return FLS_ERR_UNSUPPORTED;  // upstream always asks for 5 (loam_point_to_plane_ivox.h:269)
-        if (c->max_iterations > 255) return FLS_ERR_UNSUPPORTED;  // 8-bit iteration field of the hand-over tags (fls_gn.cuh)
     } else if (c->method == FLS_NDT) {
         if (!(c->ndt_voxel_size > 0) || !(c->ndt_voxel_size < 1e300) || !(c->ndt_outlier_thres < 1e300) || !(c->source_cloud_filter_size > 0.f) ||
             c->ndt_capacity <= 0 || c->ndt_capacity == 2147483647 || c->ndt_min_points_in_voxel < 0 || c->ndt_min_points_in_voxel > 64)

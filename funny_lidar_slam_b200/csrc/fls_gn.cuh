@@ -24,9 +24,9 @@ struct GnParams {
 // Control block of a persistent (one launch per Match) Gauss-Newton loop
 struct GnLoopCtl {
     GnState* state;
-    double* rows;    // [gridDim.x][32] per-CTA partial sums
-    int* sync;       // [2*max_iterations]: slot 2*it+1 counts the CTAs that finished iteration `it`
-    int* sync_flag;  // iterations completed (release flag)
+    uint4* ll_rows;     // [gridDim.x][32] LL records: per-CTA partial sums
+    uint4* ll_pose;     // [kLlPoseLen] LL records: next pose + stop word
+    unsigned tag_base;  // Match epoch << 8
     GnParams gp;
     fls_iter_log* log;
     int log_cap;
@@ -224,15 +224,17 @@ __device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p,
 }
 
 // Tail of one iteration of a persistent GN loop (all threads of all CTAs call it with their per-thread sums):
-// block reduction -> CTA row -> ONE fence + ONE atomic per CTA -> the CTA that arrives last folds every row in a fixed
-// order, runs gn_step (which publishes the pose and releases the flag) -> everybody else waits on the flag.
-// Needs co-resident CTAs (cooperative launch).  Returns true when the loop is finished.
+// block reduction -> CTA row published as LL records (no fence, no atomic) -> CTA 0 sweeps the rows until every tag matches,
+// folds them in a fixed order, runs gn_step and publishes the next pose + stop word as LL records -> everybody polls that
+// record.  Needs co-resident CTAs (cooperative launch).  On return s_pose[0..11] (shared memory, row-major R then t) holds
+// the pose of the next iteration; returns true when the loop is finished.
 template <int BLOCK>
-__device__ __forceinline__ bool gn_handover(double (&acc)[kNumAcc], const GnLoopCtl& c, int it) {
+__device__ __forceinline__ bool gn_handover(double (&acc)[kNumAcc], const GnLoopCtl& c, int it, double* s_pose) {
     constexpr int W = BLOCK / 32;
     __shared__ double s_red[W][kAccStride];
-    __shared__ int s_last;
+    __shared__ int s_stop;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned tag = c.tag_base | (unsigned)(it + 1);
 #pragma unroll
     for (int k = 0; k < kNumAcc; ++k) {
         double v = acc[k];
@@ -246,28 +248,51 @@ __device__ __forceinline__ bool gn_handover(double (&acc)[kNumAcc], const GnLoop
         double v = 0;
 #pragma unroll
         for (int w = 0; w < W; ++w) v += s_red[w][lane];
-        c.rows[(size_t)blockIdx.x * 32 + lane] = v;
-        __threadfence();
-        int last = 0;
-        if (lane == 0) last = (atomicAdd(&c.sync[2 * it + 1], 1) == (int)gridDim.x - 1) ? 1 : 0;
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (lane == 0) s_last = last;
+        ll_store(c.ll_rows + (size_t)blockIdx.x * 32 + lane, v, tag);
     }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    if (blockIdx.x == 0) {
+        GnPre pre;
+        if (threadIdx.x == 0) gn_load(c.state, pre);
+        __syncthreads();  // s_red is free again
         const int nrows = (int)gridDim.x;
-        int r = warp;
-        for (; r + 3 * W < nrows; r += 4 * W) {
-            a0 += __ldcg(&c.rows[(size_t)r * 32 + lane]);
-            a1 += __ldcg(&c.rows[(size_t)(r + W) * 32 + lane]);
-            a2 += __ldcg(&c.rows[(size_t)(r + 2 * W) * 32 + lane]);
-            a3 += __ldcg(&c.rows[(size_t)(r + 3 * W) * 32 + lane]);
+        double sum;
+        for (;;) {
+            bool ok = true;
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            int r = warp;
+            for (; r + 7 * W < nrows; r += 8 * W) {  // 8 independent 16-byte loads in flight per lane
+                double v0, v1, v2, v3, v4, v5, v6, v7;
+                const bool k0 = ll_load(c.ll_rows + (size_t)r * 32 + lane, tag, v0);
+                const bool k1 = ll_load(c.ll_rows + (size_t)(r + W) * 32 + lane, tag, v1);
+                const bool k2 = ll_load(c.ll_rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
+                const bool k3 = ll_load(c.ll_rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
+                const bool k4 = ll_load(c.ll_rows + (size_t)(r + 4 * W) * 32 + lane, tag, v4);
+                const bool k5 = ll_load(c.ll_rows + (size_t)(r + 5 * W) * 32 + lane, tag, v5);
+                const bool k6 = ll_load(c.ll_rows + (size_t)(r + 6 * W) * 32 + lane, tag, v6);
+                const bool k7 = ll_load(c.ll_rows + (size_t)(r + 7 * W) * 32 + lane, tag, v7);
+                ok = ok && k0 && k1 && k2 && k3 && k4 && k5 && k6 && k7;
+                a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+                a0 += v4; a1 += v5; a2 += v6; a3 += v7;
+            }
+            for (; r + 3 * W < nrows; r += 4 * W) {
+                double v0, v1, v2, v3;
+                const bool k0 = ll_load(c.ll_rows + (size_t)r * 32 + lane, tag, v0);
+                const bool k1 = ll_load(c.ll_rows + (size_t)(r + W) * 32 + lane, tag, v1);
+                const bool k2 = ll_load(c.ll_rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
+                const bool k3 = ll_load(c.ll_rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
+                ok = ok && k0 && k1 && k2 && k3;
+                a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+            }
+            for (; r < nrows; r += W) {
+                double v0;
+                ok = ok && ll_load(c.ll_rows + (size_t)r * 32 + lane, tag, v0);
+                a0 += v0;
+            }
+            sum = (a0 + a1) + (a2 + a3);
+            if (__all_sync(0xffffffffu, ok)) break;
+            __nanosleep(100);
         }
-        for (; r < nrows; r += W) a0 += __ldcg(&c.rows[(size_t)r * 32 + lane]);
-        __syncthreads();  // everyone is done reading s_red from the block reduction
-        s_red[warp][lane] = (a0 + a1) + (a2 + a3);
+        s_red[warp][lane] = sum;
         __syncthreads();
         if (warp == 0) {
             double t = 0;
@@ -276,14 +301,17 @@ __device__ __forceinline__ bool gn_handover(double (&acc)[kNumAcc], const GnLoop
             __syncwarp();
             s_red[0][lane] = t;
             __syncwarp();
-            if (lane == 0) gn_step(c.state, s_red[0], c.gp, c.log, c.log_cap, c.sync_flag, it + 1);
+            if (lane == 0) gn_step_pre(c.state, pre, s_red[0], c.gp, c.log, c.log_cap, nullptr, 0, c.ll_pose, tag);
         }
-    } else if (threadIdx.x == 0) {
-        while (*reinterpret_cast<volatile int*>(c.sync_flag) < it + 1) __nanosleep(200);
-        __threadfence();
+    }
+    if (threadIdx.x < 13) {
+        double v;
+        while (!ll_load(c.ll_pose + threadIdx.x, tag, v)) __nanosleep(100);
+        if (threadIdx.x < 12) s_pose[threadIdx.x] = v;
+        else s_stop = v != 0.0;
     }
     __syncthreads();
-    return __ldcg(&c.state->done) != 0;
+    return s_stop != 0;
 }
 #endif
 

@@ -102,12 +102,10 @@ __global__ void __launch_bounds__(BLOCK) icp_gn_kernel(IcpArgs a, GnLoopCtl ctl)
     const int sub = threadIdx.x & (kIcpLanes - 1);
     const unsigned group_mask = ((1u << kIcpLanes) - 1u) << ((threadIdx.x & 31) & ~(kIcpLanes - 1));
     constexpr int kPerBlock = BLOCK / kIcpLanes;
-    for (int it = 0; it < ctl.gp.max_iterations; ++it) {
-        if (threadIdx.x < 12) {
-            const double v = threadIdx.x < 9 ? __ldcg(&a.state->R[threadIdx.x]) : __ldcg(&a.state->t[threadIdx.x - 9]);
-            s_pose[threadIdx.x] = v;
-            s_posef[threadIdx.x] = (float)v;  // R.cast<float>(), t.cast<float>()  (pointcloud_utility.h:145-146)
-        }
+    if (threadIdx.x < 12) s_pose[threadIdx.x] = threadIdx.x < 9 ? __ldcg(&a.state->R[threadIdx.x]) : __ldcg(&a.state->t[threadIdx.x - 9]);
+    __syncthreads();
+    for (int it = 0; it < ctl.gp.max_iterations; ++it) {  // the hand-over leaves the next pose in s_pose
+        if (threadIdx.x < 12) s_posef[threadIdx.x] = (float)s_pose[threadIdx.x];  // R.cast<float>(), t.cast<float>()  (pointcloud_utility.h:145-146)
         __syncthreads();
         double acc[kNumAcc];
 #pragma unroll
@@ -153,7 +151,7 @@ __global__ void __launch_bounds__(BLOCK) icp_gn_kernel(IcpArgs a, GnLoopCtl ctl)
                 acc[kAccRes] += sqrt(e0 * e0 + e1 * e1 + e2 * e2);  // total_res += error.norm()  (:126)
             }
         }
-        if (gn_handover<BLOCK>(acc, ctl, it)) break;
+        if (gn_handover<BLOCK>(acc, ctl, it, s_pose)) break;
     }
 }
 

@@ -126,9 +126,9 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) loam_gn_kernel(LoamArgs a, GnLoopCtl ctl) {
     __shared__ double s_pose[12];
     const int n_total = a.n_corner + a.n_planar;
-    for (int it = 0; it < ctl.gp.max_iterations; ++it) {
-        if (threadIdx.x < 12) s_pose[threadIdx.x] = threadIdx.x < 9 ? __ldcg(&a.state->R[threadIdx.x]) : __ldcg(&a.state->t[threadIdx.x - 9]);
-        __syncthreads();
+    if (threadIdx.x < 12) s_pose[threadIdx.x] = threadIdx.x < 9 ? __ldcg(&a.state->R[threadIdx.x]) : __ldcg(&a.state->t[threadIdx.x - 9]);
+    __syncthreads();
+    for (int it = 0; it < ctl.gp.max_iterations; ++it) {  // the hand-over leaves the next pose in s_pose
         double acc[kNumAcc];
 #pragma unroll
         for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.0;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(BLOCK) loam_gn_kernel(LoamArgs a, GnLoopCtl ct
                 else acc[kAccValid] += 1.0;           // number_valid_planar_ (the < 50 failure test)
             }
         }
-        if (gn_handover<BLOCK>(acc, ctl, it)) break;
+        if (gn_handover<BLOCK>(acc, ctl, it, s_pose)) break;
     }
 }
 

@@ -216,10 +216,10 @@ __global__ void ndt_update_kernel(NdtUpdateArgs a, int* overflow) {
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) ndt_gn_kernel(NdtArgs a, GnLoopCtl ctl) {
     __shared__ double s_pose[12];
-    for (int it = 0; it < ctl.gp.max_iterations; ++it) {
     if (threadIdx.x < 9) s_pose[threadIdx.x] = __ldcg(&a.state->R[threadIdx.x]);
     else if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(&a.state->t[threadIdx.x - 9]);
     __syncthreads();
+    for (int it = 0; it < ctl.gp.max_iterations; ++it) {  // the hand-over leaves the next pose in s_pose
     double acc[kNumAcc];
 #pragma unroll
     for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.0;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(BLOCK) ndt_gn_kernel(NdtArgs a, GnLoopCtl ctl)
             acc[kAccRes] += chis;
         }
     }
-    if (gn_handover<BLOCK>(acc, ctl, it)) break;
+    if (gn_handover<BLOCK>(acc, ctl, it, s_pose)) break;
     }
 }
 
