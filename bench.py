@@ -142,7 +142,9 @@ def secondary_kernels(device: int, peak: float, log, steps: int = 6):
             # input: dx*dy*dz > INT_MAX), exactly 10 GN iterations (thresholds 0)
             ("ndt_128line_10iters", _abi.FLS_NDT, "os128", 0.05, 0.5,
              dict(ndt_capacity=2000000, source_cloud_filter_size=0.01, max_iterations=10, position_converge_thres=0.0, rotation_converge_thres=0.0)),
-            ("icp_16line", _abi.FLS_ICP_P2P, "vlp16", 0.3, 3.0, {})):
+            ("icp_16line", _abi.FLS_ICP_P2P, "vlp16", 0.3, 3.0, {}),
+            # K5: kd-tree point-to-plane (exact unbounded 5-NN on the grid); the raw 16-line scan stands in for the planar cloud
+            ("loam_kdtree_16line", _abi.FLS_P2PLANE_KNN, "vlp16", 0.1, 1.0, {})):
         scans = [synth.make_scan(world, traj[3 + 2 * i], sensor, seed=300 + i)["points"] for i in range(3)]
         guesses = [synth.perturb_pose(traj[3 + 2 * i], seed=900 + i, dpos=dpos, drot_deg=drot) for i in range(3)]
         cfg = _abi.default_config(method, device=device, flags=_abi.FLS_FLAG_PROFILE, **extra)

@@ -9,8 +9,8 @@ namespace fls {
 
 static constexpr int kP2PlaneBlock = 768;  // default shape of the persistent LOAM-iVox kernel: one 24-warp CTA per SM (fls_p2plane.cu)
 static constexpr int kNdtBlock = 512;  // few CTA rows for the folder: a dense scan fills the device with ~150-300 CTAs instead of > 1000
-static constexpr int kIcpBlock = 128;
-static constexpr int kLoamBlock = 128;
+static constexpr int kIcpBlock = 512;   // 64 queries x 8 lanes per CTA: few rows for the folder
+static constexpr int kLoamBlock = 256;
 
 static constexpr int kMaxBatch = 64;  // scans per fls_match_batch call
 

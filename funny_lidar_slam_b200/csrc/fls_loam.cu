@@ -37,8 +37,29 @@ __device__ __forceinline__ void scan_cell(const LoamGrid& g, int cx, int cy, int
     }
 }
 
-// exact 5-NN; `gate` = squared distance beyond which the caller rejects the point anyway (INFINITY: none)
-__device__ __noinline__ void grid_knn5(const LoamGrid& g, float qx, float qy, float qz, float gate, Top5& nn, unsigned& n_cand) {
+// kLoamLanes lanes share one query: lane `sub` visits every kLoamLanes-th cell, keeps a PRIVATE top-5 (the private lists
+// of a group are disjoint), and the group's answer is their butterfly merge.
+static constexpr int kLoamLanes = 8;
+
+__device__ __forceinline__ void merge_group(Top5& m, unsigned group_mask) {
+#pragma unroll
+    for (int o = kLoamLanes / 2; o > 0; o >>= 1) {
+        const float e0 = __shfl_xor_sync(group_mask, m.d0, o), e1 = __shfl_xor_sync(group_mask, m.d1, o), e2 = __shfl_xor_sync(group_mask, m.d2, o),
+                    e3 = __shfl_xor_sync(group_mask, m.d3, o), e4 = __shfl_xor_sync(group_mask, m.d4, o);
+        const unsigned j0 = __shfl_xor_sync(group_mask, m.k0, o), j1 = __shfl_xor_sync(group_mask, m.k1, o), j2 = __shfl_xor_sync(group_mask, m.k2, o),
+                       j3 = __shfl_xor_sync(group_mask, m.k3, o), j4 = __shfl_xor_sync(group_mask, m.k4, o);
+        m.push(e0, j0);
+        m.push(e1, j1);
+        m.push(e2, j2);
+        m.push(e3, j3);
+        m.push(e4, j4);
+    }
+}
+
+// exact 5-NN; `gate` = squared distance beyond which the caller rejects the point anyway (INFINITY: none).
+// Called by all lanes of a group with the same query; every lane returns the group's merged result in `nn`.
+__device__ __noinline__ void grid_knn5(const LoamGrid& g, int sub, unsigned group_mask, float qx, float qy, float qz, float gate, Top5& nn,
+                                       unsigned& n_cand) {
     nn.init();
     n_cand = 0;
     if (g.n_pts < 5u) return;  // the tree cannot return 5 neighbours
@@ -48,33 +69,41 @@ __device__ __noinline__ void grid_knn5(const LoamGrid& g, float qx, float qy, fl
     // distance (in cells) from the query to the nearest face of its own cell
     const float fx = ux - fx0, fy = uy - fy0, fz = uz - fz0;
     const float face = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
+    Top5 mine;
+    mine.init();
 #pragma unroll 1
-    for (int s = 0; s < 27; ++s) scan_cell(g, kx + c_stencil[s][0], ky + c_stencil[s][1], kz + c_stencil[s][2], qx, qy, qz, nn, n_cand);
+    for (int s = sub; s < 27; s += kLoamLanes) scan_cell(g, kx + c_stencil[s][0], ky + c_stencil[s][1], kz + c_stencil[s][2], qx, qy, qz, mine, n_cand);
 #pragma unroll 1
     for (int R = 1;; ++R) {
+        nn = mine;
+        merge_group(nn, group_mask);
         const float edge = ((float)R + face) * g.cell * 0.9995f;  // conservative: keys are floor(fl(p * inv_cell))
         const float b2 = edge * edge;
         if (nn.full() && nn.d4 <= b2) return;  // settled
         if (b2 > gate) return;                 // everything unseen lies beyond the gate
         if (R >= kMaxShell) break;
         const int S = R + 1;  // ring of Chebyshev radius S
+        int cell = 0;
 #pragma unroll 1
         for (int dz = -S; dz <= S; ++dz)
 #pragma unroll 1
             for (int dy = -S; dy <= S; ++dy) {
                 const bool face_row = (dz == -S || dz == S || dy == -S || dy == S);
 #pragma unroll 1
-                for (int dx = -S; dx <= S; dx += (face_row ? 1 : 2 * S)) scan_cell(g, kx + dx, ky + dy, kz + dz, qx, qy, qz, nn, n_cand);
+                for (int dx = -S; dx <= S; dx += (face_row ? 1 : 2 * S), ++cell)
+                    if ((cell & (kLoamLanes - 1)) == sub) scan_cell(g, kx + dx, ky + dy, kz + dz, qx, qy, qz, mine, n_cand);
             }
     }
     // exhaustive scan (far query or very sparse map)
-    nn.init();
+    mine.init();
 #pragma unroll 1
-    for (unsigned j = 0; j < g.n_pts; ++j) {
+    for (unsigned j = (unsigned)sub; j < g.n_pts; j += kLoamLanes) {
         const float4 p = __ldg(g.pts + j);
-        nn.push(dist2_ref(p.x, p.y, p.z, qx, qy, qz), j);
+        mine.push(dist2_ref(p.x, p.y, p.z, qx, qy, qz), j);
     }
-    n_cand += g.n_pts;
+    n_cand += g.n_pts / kLoamLanes;
+    nn = mine;
+    merge_group(nn, group_mask);
 }
 
 // LoamFull::CornerMatch per point (:219-270): line through the 5 neighbours by the principal axis of their covariance
@@ -126,13 +155,16 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) loam_gn_kernel(LoamArgs a, GnLoopCtl ctl) {
     __shared__ double s_pose[12];
     const int n_total = a.n_corner + a.n_planar;
+    const int sub = threadIdx.x & (kLoamLanes - 1);
+    const unsigned group_mask = ((1u << kLoamLanes) - 1u) << ((threadIdx.x & 31) & ~(kLoamLanes - 1));
+    constexpr int kPerBlock = BLOCK / kLoamLanes;
     if (threadIdx.x < 12) s_pose[threadIdx.x] = threadIdx.x < 9 ? __ldcg(&a.state->R[threadIdx.x]) : __ldcg(&a.state->t[threadIdx.x - 9]);
     __syncthreads();
     for (int it = 0; it < ctl.gp.max_iterations; ++it) {  // the hand-over leaves the next pose in s_pose
         double acc[kNumAcc];
 #pragma unroll
         for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.0;
-        for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n_total; i += gridDim.x * BLOCK) {
+        for (int i = blockIdx.x * kPerBlock + threadIdx.x / kLoamLanes; i < n_total; i += gridDim.x * kPerBlock) {
             const bool is_corner = i < a.n_corner;
             const float4 sp = is_corner ? a.corner[i] : a.planar[i - a.n_corner];
             // pcl::transformPoint with the double transform, stored back as fp32 (:219-220, :284-285, kdtree :211-212)
@@ -142,16 +174,17 @@ __global__ void __launch_bounds__(BLOCK) loam_gn_kernel(LoamArgs a, GnLoopCtl ct
             const LoamGrid& g = is_corner ? a.corner_map : a.planar_map;
             Top5 nn;
             unsigned n_cand;
-            grid_knn5(g, qx, qy, qz, a.gate, nn, n_cand);
+            grid_knn5(g, sub, group_mask, qx, qy, qz, a.gate, nn, n_cand);
             acc[kAccCand] += (double)n_cand;
             double J[6], r = 0.0;
             bool use = false;
-            if (nn.full() && !((double)nn.d4 > a.search_thres)) {  // :227 / :291 (search_thres = +inf for the kd-tree point-to-plane plug-in)
+            if (sub == 0 && nn.full() && !((double)nn.d4 > a.search_thres)) {  // :227 / :291 (search_thres = +inf for the kd-tree point-to-plane plug-in)
                 const unsigned js[5] = {nn.k0, nn.k1, nn.k2, nn.k3, nn.k4};
                 unsigned fb = 0;
                 use = is_corner ? corner_term(g.pts, js, sp, qx, qy, qz, s_pose, a.line_ratio, J, r)
                                 : plane_term(g.pts, js, sp, qx, qy, qz, s_pose, a.plane_thres, J, r, fb);
             }
+            if (sub != 0) continue;  // lane 0 of the group owns the point's record and sums
             double* rec = a.rec + (size_t)i * 8;
             if (use) {
 #pragma unroll
@@ -195,7 +228,8 @@ int loam_grid_blocks(int n, int device) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loam_gn_kernel<kLoamBlock>, kLoamBlock, 0);
         cap[device] = sms * (per_sm > 0 ? per_sm : 1);
     }
-    const int need = (n + kLoamBlock - 1) / kLoamBlock;
+    const int per_block = kLoamBlock / kLoamLanes;
+    const int need = (n + per_block - 1) / per_block;
     const int c = (device >= 0 && device < 64) ? cap[device] : 148;
     const int g = need < c ? need : c;
     return g > 0 ? g : 1;
