@@ -590,7 +590,7 @@ __global__ void ivox_insert_scatter_kernel(const unsigned char* __restrict__ cls
 // rows to fold; with a batch the fold is hidden behind the other scans.  FLS_P2PLANE_BLOCK=96|192|384|768 overrides.
 template <int BLOCK>
 struct P2PlaneShape {
-    static constexpr int kMinB = 768 / BLOCK;
+    static constexpr int kMinB = BLOCK >= 768 ? 1 : 768 / BLOCK;
     static const void* fn() { return (const void*)p2plane_gn_kernel<BLOCK, kMinB>; }
     static size_t smem() { return (size_t)(BLOCK / 32) * 32 * kRecW * sizeof(double); }
     static int max_grid(int sms) {
@@ -611,7 +611,7 @@ int p2plane_block() {
     if (!block) {
         const char* e = std::getenv("FLS_P2PLANE_BLOCK");
         const int v = e ? std::atoi(e) : 0;
-        block = (v == 96 || v == 192 || v == 384 || v == 768) ? v : kP2PlaneBlock;
+        block = (v == 96 || v == 192 || v == 384 || v == 768 || v == 1024) ? v : kP2PlaneBlock;
     }
     return block;
 }
@@ -626,6 +626,7 @@ int p2plane_max_grid(int device) {
         case 96: g = P2PlaneShape<96>::max_grid(sms); break;
         case 192: g = P2PlaneShape<192>::max_grid(sms); break;
         case 384: g = P2PlaneShape<384>::max_grid(sms); break;
+        case 1024: g = P2PlaneShape<1024>::max_grid(sms); break;
         default: g = P2PlaneShape<768>::max_grid(sms); break;
     }
     if (device >= 0 && device < 64) cached[device] = g;
@@ -649,6 +650,7 @@ void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st) {
         case 96: P2PlaneShape<96>::launch(grid, params, st); break;
         case 192: P2PlaneShape<192>::launch(grid, params, st); break;
         case 384: P2PlaneShape<384>::launch(grid, params, st); break;
+        case 1024: P2PlaneShape<1024>::launch(grid, params, st); break;
         default: P2PlaneShape<768>::launch(grid, params, st); break;
     }
 }
