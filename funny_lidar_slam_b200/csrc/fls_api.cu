@@ -157,7 +157,6 @@ static GnLoopCtl make_ctl(Handle& h, int method, int grid, int min_effective) {
     c.gp.method = method;
     c.gp.max_iterations = h.cfg.max_iterations;
     c.gp.min_effective = min_effective;
-    c.gp.n_blocks = grid;
     c.gp.rot_thres = h.cfg.rotation_converge_thres;
     c.gp.pos_thres = h.cfg.position_converge_thres;
     c.log = h.log.p;
@@ -262,7 +261,6 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
     a.gp.method = FLS_P2PLANE_IVOX;
     a.gp.max_iterations = cfg.max_iterations;
     a.gp.min_effective = 50;
-    a.gp.n_blocks = grid;
     a.gp.rot_thres = cfg.rotation_converge_thres;
     a.gp.pos_thres = cfg.position_converge_thres;
     a.log_cap = log_cap;
@@ -389,7 +387,6 @@ int Handle::match_ndt(const float4* d_in, size_t n_in, double* T, int* converged
     a.map = ndt.view();
     a.outlier_thres = cfg.ndt_outlier_thres;
     a.state = state.p;
-    a.partials = partials.p;
     // roofline accounting: 16 B source point + 7 x 16 B slot probes per point-iteration,
     // 80 B voxel record per estimated voxel hit; the 6x6 sums are fused (no per-point output).
     per_point_iter_bytes = 16 + 16LL * 7;
@@ -502,7 +499,6 @@ int Handle::match_icp(const float4* d_in, size_t n_in, double* T, int* converged
     a.map = grid_view(icp_grid);
     a.max_corr = cfg.icp_max_correspond_distance;
     a.state = state.p;
-    a.partials = partials.p;
     // roofline accounting: 16 B source point + 27 x 16 B slot probes, 16 B per scanned map record
     per_point_iter_bytes = 16 + 16LL * 27;
     per_cand_bytes = 16;

@@ -17,7 +17,6 @@ struct GnParams {
     int method;  // fls_method: selects dx layout, update side, solver, stop rule
     int max_iterations;
     int min_effective;  // NDT: min_effective_pts; LOAM: 50 valid planar points
-    int n_blocks;       // rows of the partial-sum matrix produced by the residual kernel
     double rot_thres, pos_thres;
 };
 
@@ -32,34 +31,9 @@ struct GnLoopCtl {
     int log_cap;
 };
 
-// state initialisation (+ optional zeroing of the hand-over counters) in one launch
-void launch_gn_init(GnState* d_state, const double* T_colmajor, cudaStream_t st, int* d_sync = nullptr, int n_sync = 0);
-void launch_gn_solve(GnState* d_state, const double* d_partials, const GnParams& p, fls_iter_log* d_log, int log_capacity, cudaStream_t st);
+void launch_gn_init(GnState* d_state, const double* T_colmajor, cudaStream_t st);
 
 #ifdef __CUDACC__
-// Reduce acc[kNumAcc] over the thread block (blockDim.x multiple of 32, <= 1024) and write one row of the
-// partial-sum matrix.  Fixed order: lanes by xor-butterfly, then warps 0..W-1 => bitwise reproducible.
-template <int BLOCK>
-__device__ __forceinline__ void block_reduce_store(double (&acc)[kNumAcc], double* __restrict__ partial_row) {
-    constexpr int W = BLOCK / 32;
-    __shared__ double s_red[W][kAccStride];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < kNumAcc; ++k) {
-        double v = acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[warp][k] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < kNumAcc) {
-        double v = 0;
-#pragma unroll
-        for (int w = 0; w < W; ++w) v += s_red[w][threadIdx.x];
-        partial_row[threadIdx.x] = v;
-    }
-}
-
 // ---- flag-in-data hand-over ("LL" records) ---------------------------------------------------------------------------
 // A 16-byte record {lo32, tag, hi32, tag} carries one double together with the tag of the iteration that produced it.
 // Each 8-byte half is a single-copy-atomic store, so a reader that sees the expected tag in BOTH halves has the value —
@@ -98,10 +72,9 @@ __device__ __forceinline__ void gn_load(const GnState* s, GnPre& q) {
 
 // One Gauss-Newton step from the reduced totals `tot[kNumAcc]`: fills H/g, solves, updates the pose in `s`,
 // applies the plug-in's stop rule.  Executed by a single thread: the arithmetic runs on locals, what the other CTAs wait
-// for (pose + done) goes out first — as LL records when `ll_pose` is given, else as state stores + release flag — and
-// the bookkeeping follows.
+// for (pose + stop word, as LL records) goes out first and the bookkeeping follows.
 __device__ inline void gn_step_pre(GnState* s, const GnPre& q, const double* tot, const GnParams& p, fls_iter_log* log, int log_cap,
-                                   int* release_flag, int release_value, uint4* ll_pose, unsigned ll_tag) {
+                                   uint4* ll_pose, unsigned ll_tag) {
     double R[9], t[3];
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = q.R[i];
@@ -181,10 +154,6 @@ __device__ inline void gn_step_pre(GnState* s, const GnPre& q, const double* tot
 #pragma unroll
     for (int i = 0; i < 3; ++i) s->t[i] = t[i];
     if (stop) s->done = 1;
-    if (release_flag) {
-        __threadfence();
-        atomicExch(release_flag, release_value);
-    }
     // pose before the update (LOAM-iVox map insertion rule)
 #pragma unroll
     for (int i = 0; i < 9; ++i) s->Rprev[i] = q.R[i];
@@ -214,13 +183,6 @@ __device__ inline void gn_step_pre(GnState* s, const GnPre& q, const double* tot
         L.sum_residual = sum_res;
         L.n_valid = n_valid;
     }
-}
-
-__device__ inline void gn_step(GnState* s, const double* tot, const GnParams& p, fls_iter_log* log, int log_cap, int* release_flag = nullptr,
-                               int release_value = 0) {
-    GnPre q;
-    gn_load(s, q);
-    gn_step_pre(s, q, tot, p, log, log_cap, release_flag, release_value, nullptr, 0u);
 }
 
 // Tail of one iteration of a persistent GN loop (all threads of all CTAs call it with their per-thread sums):
@@ -301,7 +263,7 @@ __device__ __forceinline__ bool gn_handover(double (&acc)[kNumAcc], const GnLoop
             __syncwarp();
             s_red[0][lane] = t;
             __syncwarp();
-            if (lane == 0) gn_step_pre(c.state, pre, s_red[0], c.gp, c.log, c.log_cap, nullptr, 0, c.ll_pose, tag);
+            if (lane == 0) gn_step_pre(c.state, pre, s_red[0], c.gp, c.log, c.log_cap, c.ll_pose, tag);
         }
     }
     if (threadIdx.x < 13) {

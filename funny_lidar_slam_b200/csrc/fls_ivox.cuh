@@ -54,79 +54,4 @@ __host__ __device__ __forceinline__ void morton_decode(unsigned long long m, int
     z = (int)compact21(m >> 2) - (1 << 20);
 }
 
-struct Knn5 {
-    float d0, d1, d2, d3, d4;
-    unsigned j0, j1, j2, j3, j4;
-    __device__ __forceinline__ void init() {
-        d0 = d1 = d2 = d3 = d4 = INFINITY;
-        j0 = j1 = j2 = j3 = j4 = 0xffffffffu;
-    }
-    // insert keeping ascending (d, visit order): a later candidate never passes an equal earlier one
-    __device__ __forceinline__ void push(float d, unsigned j) {
-        if (!(d < d4)) return;
-        d4 = d;
-        j4 = j;
-        if (d4 < d3) { float td = d3; d3 = d4; d4 = td; unsigned tj = j3; j3 = j4; j4 = tj; } else return;
-        if (d3 < d2) { float td = d2; d2 = d3; d3 = td; unsigned tj = j2; j2 = j3; j3 = tj; } else return;
-        if (d2 < d1) { float td = d1; d1 = d2; d2 = td; unsigned tj = j1; j1 = j2; j2 = tj; } else return;
-        if (d1 < d0) { float td = d0; d0 = d1; d1 = td; unsigned tj = j0; j0 = j1; j1 = tj; }
-    }
-};
-
-// IVoxMap::GetClosestPoint(pt, out, 5, max_range) (ivox_map.cpp:6-37 + voxel_grid_node.cpp:23-42 upstream), probing
-// the occupied table once per stencil voxel.  Per-voxel top-K followed by a global top-K equals the global top-K of
-// all in-range candidates, which is what is kept; the nearest ends in slot 0 (the only ordering upstream guarantees).
-// Indices refer to `pts`.
-__device__ __forceinline__ void ivox_knn5(const IvoxView& m, float qx, float qy, float qz, Knn5& nn, unsigned& n_cand, unsigned& n_hits) {
-    nn.init();
-    n_cand = 0;
-    n_hits = 0;
-    const int kx = ivox_coord(qx, m.inv_res), ky = ivox_coord(qy, m.inv_res), kz = ivox_coord(qz, m.inv_res);
-#pragma unroll 1
-    for (int s = 0; s < m.n_stencil; ++s) {
-        const unsigned long long key = pack_key(kx + c_stencil[s][0], ky + c_stencil[s][1], kz + c_stencil[s][2]);
-        unsigned start, count;
-        if (!table_find(m.tab, m.mask, key, start, count)) continue;
-        n_cand += count;
-        n_hits += 1;
-#pragma unroll 1
-        for (unsigned j = start; j < start + count; ++j) {
-            const float4 p = __ldg(m.pts + j);
-            const float d = dist2_ref(p.x, p.y, p.z, qx, qy, qz);
-            if (d < m.max_range2) nn.push(d, j);
-        }
-    }
-}
-
-// Same result through the stencil lists: one probe of the centre table, then a streaming scan of the
-// contiguous candidate run (already in visit order).  Indices refer to `lists`.
-__device__ __forceinline__ void ivox_knn5_lists(const IvoxView& m, float qx, float qy, float qz, Knn5& nn, unsigned& n_cand) {
-    nn.init();
-    n_cand = 0;
-    const unsigned long long key = pack_key(ivox_coord(qx, m.inv_res), ivox_coord(qy, m.inv_res), ivox_coord(qz, m.inv_res));
-    unsigned start, count;
-    if (!table_find(m.ctab, m.cmask, key, start, count)) return;
-    n_cand = count;
-    const float4* __restrict__ L = m.lists + start;
-    unsigned j = 0;
-#pragma unroll 1
-    for (; j + 4 <= count; j += 4) {
-        const float4 p0 = __ldg(L + j), p1 = __ldg(L + j + 1), p2 = __ldg(L + j + 2), p3 = __ldg(L + j + 3);
-        const float e0 = dist2_ref(p0.x, p0.y, p0.z, qx, qy, qz);
-        const float e1 = dist2_ref(p1.x, p1.y, p1.z, qx, qy, qz);
-        const float e2 = dist2_ref(p2.x, p2.y, p2.z, qx, qy, qz);
-        const float e3 = dist2_ref(p3.x, p3.y, p3.z, qx, qy, qz);
-        if (e0 < m.max_range2) nn.push(e0, start + j);
-        if (e1 < m.max_range2) nn.push(e1, start + j + 1);
-        if (e2 < m.max_range2) nn.push(e2, start + j + 2);
-        if (e3 < m.max_range2) nn.push(e3, start + j + 3);
-    }
-#pragma unroll 1
-    for (; j < count; ++j) {
-        const float4 p = __ldg(L + j);
-        const float d = dist2_ref(p.x, p.y, p.z, qx, qy, qz);
-        if (d < m.max_range2) nn.push(d, start + j);
-    }
-}
-
 }  // namespace fls

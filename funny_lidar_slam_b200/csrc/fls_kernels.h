@@ -61,7 +61,6 @@ struct NdtArgs {
     NdtView map;
     double outlier_thres;
     GnState* state;
-    double* __restrict__ partials;
 };
 int ndt_grid(int n, int device);  // co-resident grid of the persistent kernel
 void launch_ndt_loop(const NdtArgs& a, const GnLoopCtl& ctl, int grid, cudaStream_t st);
@@ -72,7 +71,6 @@ struct IcpArgs {
     IvoxView map;  // floor-keyed search grid over the voxel-filtered local map
     double max_corr;
     GnState* state;
-    double* __restrict__ partials;
 };
 int icp_grid_blocks(int n, int device);
 void launch_icp_loop(const IcpArgs& a, const GnLoopCtl& ctl, int grid, cudaStream_t st);
