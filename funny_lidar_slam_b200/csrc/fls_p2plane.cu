@@ -205,14 +205,18 @@ __device__ __forceinline__ bool p2plane_point(const IvoxView& map, const float4 
 // columns of the per-point staging record
 constexpr int kRecAd = 6, kRecValid = 7, kRecCand = 8, kRecHits = 9, kRecOne = 10, kRecW = 12;
 
+constexpr int kVisitGroup = 4;  // scans whose chunks a warp works through between two CTA barriers
+
 template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs a) {
     constexpr int W = BLOCK / 32;
-    __shared__ double s_pose[12];
+    constexpr int V = kVisitGroup < W ? kVisitGroup : W;
     extern __shared__ __align__(16) unsigned char s_dyn[];
     double (*s_rec)[32][kRecW] = reinterpret_cast<double (*)[32][kRecW]>(s_dyn);  // [W][32][kRecW] per-lane staging records
-    __shared__ double s_red[W][32];
-    __shared__ int s_stop;
+    __shared__ double s_pose[V][12];
+    __shared__ double s_part[V][W][32];  // per scan of the group: every warp's 32 sums
+    __shared__ double s_red[W][32];      // fold scratch of the folding CTA
+    __shared__ int s_stop[V];
     __shared__ unsigned char s_iter[kMaxBatch];  // iterations this CTA has completed of every scan (255 = scan finished)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
@@ -243,43 +247,66 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
     __syncthreads();
 
     // One launch serves a batch of independent scans and EVERY CTA works on EVERY scan: the grid sweeps the scans round-
-    // robin, one Gauss-Newton iteration of one scan per visit.  A visit ends with this CTA's row of partial sums going out
-    // as LL records; only the scan's folding CTA waits for the other rows, solves and publishes the next pose — everybody
-    // else moves straight on to the next scan, and by the time the sweep returns to this scan its pose has long been
-    // published.  The hand-over latency of one scan is hidden behind the work on the others; finished scans drop out of
-    // the sweep, so the remaining ones simply come round faster (no static partition of the SMs, no idle CTAs).
+    // robin, one Gauss-Newton iteration of each scan per visit, up to V scans per visit.  Inside a visit a warp works
+    // through its chunk of every scan of the group back to back — the CTA barrier that ends the visit then waits for the
+    // slowest SUM of V chunks instead of V times for the slowest chunk.  A visit ends with this CTA's rows of partial sums
+    // going out as LL records; only a scan's folding CTA waits for the other rows, solves and publishes the next pose —
+    // everybody else moves straight on, and by the time the sweep returns to a scan its pose has long been published.  The
+    // hand-over latency of one scan is hidden behind the work on the others; finished scans drop out of the sweep, so the
+    // remaining ones come round faster (no static partition of the SMs, no idle CTAs).
     // With a single scan the sweep degenerates to: work, publish, wait for the pose.
     int n_left = a.n_scans;
+    int next = 0;  // where the sweep continues
     while (n_left > 0) {
-        for (int s = 0; s < a.n_scans; ++s) {
+        // ---- the group: the next (up to V) unfinished scans in round-robin order (uniform: s_iter is shared) -------------
+        int gs[V], git[V], nv = 0;
+        for (int k = 0; k < a.n_scans && nv < V; ++k) {
+            const int s = (next + k) % a.n_scans;
             const int it = s_iter[s];
             if (it == 255) continue;
-            const P2PlaneScan* __restrict__ sc = a.scans + s;
-            GnState* const state = sc->state;
-            // ---- pose of this iteration: the prep kernel's state for iteration 0, afterwards the LL record published by
-            // the scan's folder at the end of iteration it-1 (12 values + the stop word)
-            if (it == 0) {
-                if (threadIdx.x < 9) s_pose[threadIdx.x] = __ldcg(&state->R[threadIdx.x]);
-                else if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(&state->t[threadIdx.x - 9]);
-                if (threadIdx.x == 12) s_stop = 0;
-            } else if (threadIdx.x < 13) {
-                const unsigned ptag = sc->tag_base | (unsigned)it;
-                const uint4* ll = sc->ll_pose;
-                double v;
-                while (!ll_load(ll + threadIdx.x, ptag, v)) __nanosleep(100);
-                if (threadIdx.x < 12) s_pose[threadIdx.x] = v;
-                else s_stop = v != 0.0;
+            gs[nv] = s;
+            git[nv] = it;
+            ++nv;
+        }
+        next = (gs[nv - 1] + 1) % a.n_scans;
+        // ---- poses of this visit: the prep kernel's state for iteration 0, afterwards the LL record published by the
+        // scan's folder at the end of iteration it-1 (12 values + the stop word); 16 threads per scan of the group
+        {
+            const int v = threadIdx.x >> 4, k = threadIdx.x & 15;
+            if (v < nv && k < 13) {
+                const P2PlaneScan* __restrict__ sc = a.scans + gs[v];
+                if (git[v] == 0) {
+                    if (k < 9) s_pose[v][k] = __ldcg(&sc->state->R[k]);
+                    else if (k < 12) s_pose[v][k] = __ldcg(&sc->state->t[k - 9]);
+                    else s_stop[v] = 0;
+                } else {
+                    const unsigned ptag = sc->tag_base | (unsigned)git[v];
+                    const uint4* ll = sc->ll_pose;
+                    double val;
+                    while (!ll_load(ll + k, ptag, val)) __nanosleep(100);
+                    if (k < 12) s_pose[v][k] = val;
+                    else s_stop[v] = val != 0.0;
+                }
             }
-            __syncthreads();
-            if (s_stop) {  // uniform: the scan finished with iteration it-1
-                if (threadIdx.x == 0) s_iter[s] = 255;
-                __syncthreads();  // everybody has read s_stop; s_iter is visible before the next sweep
+        }
+        __syncthreads();
+        bool live[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            live[v] = v < nv && !s_stop[v];
+            if (v < nv && s_stop[v]) {  // uniform: the scan finished with iteration it-1
+                if (threadIdx.x == 0) s_iter[gs[v]] = 255;
                 --n_left;
-                continue;
             }
-            const unsigned tag = sc->tag_base | (unsigned)(it + 1);
+        }
+        // ---- work: this warp's chunks of every live scan of the group, no barrier in between ---------------------------
+#pragma unroll 1
+        for (int v = 0; v < nv; ++v) {
+            if (!live[v]) continue;
+            const int s = gs[v];
+            const P2PlaneScan* __restrict__ sc = a.scans + s;
             const int folder = s % G;
-            if (cta == folder && threadIdx.x == 0 && it < 16) state->dbg[it][0] = globaltimer_ns();
+            if (cta == folder && threadIdx.x == 0 && git[v] < 16) sc->state->dbg[git[v]][0] = globaltimer_ns();
             const int n = sc->n;
             const int n_chunks = (n + 31) >> 5;  // warp-sized chunks
             const float4* __restrict__ src = sc->src;
@@ -289,6 +316,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
             // the folder takes the last block of chunks: it is the CTA that stays idle when the scan has fewer chunks than
             // the grid has warps (p2plane_grid adds one CTA for that purpose)
             const int slot = (cta - folder - 1 + G) % G;
+            const double* pose = s_pose[v];
 
             double acc = 0.0;  // lane k's running sum over every chunk of this warp
             // warp-granular work loop, static round-robin over 32-point chunks: no barrier, no atomics inside
@@ -300,7 +328,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
                 unsigned n_cand = 0, n_fb = 0;
                 if (i < n) {
                     const float4 sp = src[i];
-                    bool use = p2plane_point(a.map, sp, s_pose, a.plane_thres, J, ad, n_cand, n_fb);
+                    bool use = p2plane_point(a.map, sp, pose, a.plane_thres, J, ad, n_cand, n_fb);
                     if (use) {
                         rec0[i] = make_float4((float)J[0], (float)J[1], (float)J[2], (float)J[3]);
                         rec1[i] = make_float4((float)J[4], (float)J[5], (float)ad, 1.0f);
@@ -330,81 +358,91 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
                 for (int p = 0; p < 32; ++p) acc += s_rec[warp][p][ca] * s_rec[warp][p][cb];
                 __syncwarp();
             }
-            // ---- CTA row: one LL record per sum, no fence, no atomic ------------------------------------------------------
-            s_red[warp][lane] = acc * sgn;
-            __syncthreads();
-            uint4* const rows = sc->rows;
-            if (warp == 0) {
-                double v = 0;
-#pragma unroll
-                for (int w = 0; w < W; ++w) v += s_red[w][lane];
-                ll_store(rows + (size_t)cta * 32 + lane, v, tag);
-            }
-            if (cta == folder) {
-                // ---- fold: warp w owns rows w, w+W, ...; every sweep re-reads all of them (independent loads, one L2 round
-                // trip) until each carries this iteration's tag, then the sums are taken in a fixed order — bitwise
-                // reproducible, and the fold is finished one sweep after the slowest CTA's row lands
-                GnPre pre;
-                if (threadIdx.x == 0) gn_load(state, pre);  // off the critical path: the state is stable until gn_step below
-                __syncthreads();  // s_red is free again
-                const int nrows = G;
-                double sum;
-                for (;;) {
-                    bool ok = true;
-                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                    int r = warp;
-                    for (; r + 7 * W < nrows; r += 8 * W) {  // 8 independent 16-byte loads in flight per lane
-                        double v0, v1, v2, v3, v4, v5, v6, v7;
-                        const bool k0 = ll_load(rows + (size_t)r * 32 + lane, tag, v0);
-                        const bool k1 = ll_load(rows + (size_t)(r + W) * 32 + lane, tag, v1);
-                        const bool k2 = ll_load(rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
-                        const bool k3 = ll_load(rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
-                        const bool k4 = ll_load(rows + (size_t)(r + 4 * W) * 32 + lane, tag, v4);
-                        const bool k5 = ll_load(rows + (size_t)(r + 5 * W) * 32 + lane, tag, v5);
-                        const bool k6 = ll_load(rows + (size_t)(r + 6 * W) * 32 + lane, tag, v6);
-                        const bool k7 = ll_load(rows + (size_t)(r + 7 * W) * 32 + lane, tag, v7);
-                        ok = ok && k0 && k1 && k2 && k3 && k4 && k5 && k6 && k7;
-                        a0 += v0; a1 += v1; a2 += v2; a3 += v3;
-                        a0 += v4; a1 += v5; a2 += v6; a3 += v7;
-                    }
-                    for (; r + 3 * W < nrows; r += 4 * W) {
-                        double v0, v1, v2, v3;
-                        const bool k0 = ll_load(rows + (size_t)r * 32 + lane, tag, v0);
-                        const bool k1 = ll_load(rows + (size_t)(r + W) * 32 + lane, tag, v1);
-                        const bool k2 = ll_load(rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
-                        const bool k3 = ll_load(rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
-                        ok = ok && k0 && k1 && k2 && k3;
-                        a0 += v0; a1 += v1; a2 += v2; a3 += v3;
-                    }
-                    for (; r < nrows; r += W) {
-                        double v0;
-                        ok = ok && ll_load(rows + (size_t)r * 32 + lane, tag, v0);
-                        a0 += v0;
-                    }
-                    sum = (a0 + a1) + (a2 + a3);
-                    if (__all_sync(0xffffffffu, ok)) break;
-                    __nanosleep(100);
-                }
-                s_red[warp][lane] = sum;
-                __syncthreads();
-                if (warp == 0) {
-                    if (lane == 0 && it < 16) state->dbg[it][1] = globaltimer_ns();
-                    double t = 0;
-#pragma unroll
-                    for (int w = 0; w < W; ++w) t += s_red[w][lane];
-                    __syncwarp();
-                    s_red[0][lane] = t;
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (it < 16) state->dbg[it][2] = globaltimer_ns();
-                        gn_step_pre(state, pre, s_red[0], a.gp, sc->log, a.log_cap, sc->ll_pose, tag);
-                        if (it < 16) state->dbg[it][3] = globaltimer_ns();
-                    }
-                }
-            }
-            if (threadIdx.x == 0) s_iter[s] = (unsigned char)(it + 1);
-            __syncthreads();  // s_red / s_pose / s_iter are reused by the next visit
+            s_part[v][warp][lane] = acc * sgn;
         }
+        __syncthreads();
+        // ---- CTA rows: warp v publishes the row of the group's v-th scan — LL records, no fence, no atomic ---------------
+        if (warp < nv && live[warp]) {
+            const P2PlaneScan* __restrict__ sc = a.scans + gs[warp];
+            double val = 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) val += s_part[warp][w][lane];
+            ll_store(sc->rows + (size_t)cta * 32 + lane, val, sc->tag_base | (unsigned)(git[warp] + 1));
+        }
+        // ---- folds: for the scans of the group this CTA is the folder of -------------------------------------------------
+#pragma unroll 1
+        for (int v = 0; v < nv; ++v) {
+            if (!live[v] || cta != gs[v] % G) continue;  // uniform per CTA
+            const P2PlaneScan* __restrict__ sc = a.scans + gs[v];
+            GnState* const state = sc->state;
+            const int it = git[v];
+            const unsigned tag = sc->tag_base | (unsigned)(it + 1);
+            uint4* const rows = sc->rows;
+            // warp w owns rows w, w+W, ...; every sweep re-reads all of them (independent loads, one L2 round trip) until
+            // each carries this iteration's tag, then the sums are taken in a fixed order — bitwise reproducible, and the
+            // fold is finished one sweep after the slowest CTA's row lands
+            GnPre pre;
+            if (threadIdx.x == 0) gn_load(state, pre);  // off the critical path: the state is stable until gn_step below
+            const int nrows = G;
+            double sum;
+            for (;;) {
+                bool ok = true;
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                int r = warp;
+                for (; r + 7 * W < nrows; r += 8 * W) {  // 8 independent 16-byte loads in flight per lane
+                    double v0, v1, v2, v3, v4, v5, v6, v7;
+                    const bool k0 = ll_load(rows + (size_t)r * 32 + lane, tag, v0);
+                    const bool k1 = ll_load(rows + (size_t)(r + W) * 32 + lane, tag, v1);
+                    const bool k2 = ll_load(rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
+                    const bool k3 = ll_load(rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
+                    const bool k4 = ll_load(rows + (size_t)(r + 4 * W) * 32 + lane, tag, v4);
+                    const bool k5 = ll_load(rows + (size_t)(r + 5 * W) * 32 + lane, tag, v5);
+                    const bool k6 = ll_load(rows + (size_t)(r + 6 * W) * 32 + lane, tag, v6);
+                    const bool k7 = ll_load(rows + (size_t)(r + 7 * W) * 32 + lane, tag, v7);
+                    ok = ok && k0 && k1 && k2 && k3 && k4 && k5 && k6 && k7;
+                    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+                    a0 += v4; a1 += v5; a2 += v6; a3 += v7;
+                }
+                for (; r + 3 * W < nrows; r += 4 * W) {
+                    double v0, v1, v2, v3;
+                    const bool k0 = ll_load(rows + (size_t)r * 32 + lane, tag, v0);
+                    const bool k1 = ll_load(rows + (size_t)(r + W) * 32 + lane, tag, v1);
+                    const bool k2 = ll_load(rows + (size_t)(r + 2 * W) * 32 + lane, tag, v2);
+                    const bool k3 = ll_load(rows + (size_t)(r + 3 * W) * 32 + lane, tag, v3);
+                    ok = ok && k0 && k1 && k2 && k3;
+                    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+                }
+                for (; r < nrows; r += W) {
+                    double v0;
+                    ok = ok && ll_load(rows + (size_t)r * 32 + lane, tag, v0);
+                    a0 += v0;
+                }
+                sum = (a0 + a1) + (a2 + a3);
+                if (__all_sync(0xffffffffu, ok)) break;
+                __nanosleep(100);
+            }
+            s_red[warp][lane] = sum;
+            __syncthreads();
+            if (warp == 0) {
+                if (lane == 0 && it < 16) state->dbg[it][1] = globaltimer_ns();
+                double t = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) t += s_red[w][lane];
+                __syncwarp();
+                s_red[0][lane] = t;
+                __syncwarp();
+                if (lane == 0) {
+                    if (it < 16) state->dbg[it][2] = globaltimer_ns();
+                    gn_step_pre(state, pre, s_red[0], a.gp, sc->log, a.log_cap, sc->ll_pose, tag);
+                    if (it < 16) state->dbg[it][3] = globaltimer_ns();
+                }
+            }
+            __syncthreads();  // s_red is reused by the next fold
+        }
+        if (threadIdx.x == 0)
+            for (int v = 0; v < nv; ++v)
+                if (live[v]) s_iter[gs[v]] = (unsigned char)(git[v] + 1);
+        __syncthreads();  // s_part / s_pose / s_stop / s_iter are reused by the next visit
     }
 }
 

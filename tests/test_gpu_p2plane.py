@@ -207,3 +207,31 @@ def test_batch_needs_static_map(scene16):
     g.AddCloudToLocalMap([scene16["map"]])
     with pytest.raises(FlsError):
         g.match_batch([scene16["scan"], scene16["scan"]], np.stack([scene16["guess"], scene16["guess"]]))
+
+
+def test_batch_stress_many_small_and_empty_scans(world, traj):
+    """24 scans of very different sizes (one empty, several below the 50-valid-plane failure bar) in one launch: the sweep
+    must terminate with each scan's own result — compared with separate Matches."""
+    from funny_lidar_slam_b200.registration import PointcloudCluster, Registration
+    mp = synth.make_map_from_scans(world, traj[0:12:2], "vlp16", leaf=0.3)
+    g = Registration(default_config(FLS_P2PLANE_IVOX))
+    g.AddCloudToLocalMap([mp])
+    rng = np.random.default_rng(11)
+    base = [synth.make_scan(world, traj[3 + k], "vlp16", seed=90 + k)["points"] for k in range(4)]
+    scans, guesses = [], []
+    for j in range(24):
+        k = j % 4
+        n = [0, 17, 40, 333, 1500, 5000, len(base[k])][j % 7]
+        sel = np.sort(rng.choice(len(base[k]), n, replace=False)) if n else np.zeros(0, np.int64)
+        scans.append(np.ascontiguousarray(base[k][sel]))
+        guesses.append(synth.perturb_pose(traj[3 + k], dpos=0.02 + 0.01 * (j % 5), drot_deg=0.3 + 0.2 * (j % 3), seed=200 + j))
+    conv, Tb = g.match_batch(scans, np.stack(guesses))
+    st_b = [(s.iterations, s.n_valid, s.converged) for s in g.last_batch_stats]
+    assert not conv[0] and st_b[0][1] == 0          # the empty scan fails, nothing else is disturbed
+    for j in range(24):
+        T = guesses[j].copy()
+        ok = g.Match(PointcloudCluster(planar_cloud=scans[j]), T)
+        st = g.last_stats
+        assert bool(conv[j]) == ok and st_b[j][0] == st.iterations and st_b[j][1] == st.n_valid, j
+        assert np.allclose(Tb[j], T, rtol=0, atol=1e-8), j
+    assert conv.sum() >= 12
