@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
             double acc = 0.0;  // lane k's running sum over every chunk of this warp
             // warp-granular work loop, static round-robin over 32-point chunks: no barrier, no atomics inside
             // (consecutive chunks stay in one CTA: Morton neighbours share candidate lists in L1 — spreading them over SMs
-            //  for balance was measured 35 % slower)
+            //  for balance was measured 35 % slower; letting the CTA's warps pull the V x W chunk lists of a visit from a
+            //  shared counter was measured too: 709 vs 704 us per 8-scan launch, no gain)
             for (int chunk = slot * W + warp; chunk < n_chunks; chunk += n_warps) {
                 const int i = (chunk << 5) + lane;
                 double J[6] = {0, 0, 0, 0, 0, 0}, ad = 0.0, vflag = 0.0;
