@@ -266,6 +266,11 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
     a.log_cap = log_cap;
     a.scans = d_desc;
     a.n_scans = B;
+    {
+        const char* e = std::getenv("FLS_VISIT_GROUP");
+        const int v = e ? std::atoi(e) : 8;  // measured at batch 8: group 2 / 3 / 4 / 6 / 8 -> 783 / 734 / 703 / 724 / 687 us per launch
+        a.visit_group = v < 1 ? 1 : (v > 8 ? 8 : v);
+    }
     // roofline accounting (SURVEY.md §8d, K1 — the REFERENCE algorithm's traffic): 16 B source point + n_stencil x 16 B
     // slot probes + 32 B persistent record per point-iteration, 16 B per map record resident in the stencil voxels.
     per_point_iter_bytes = 16 + 16LL * a.map.n_stencil + 32;

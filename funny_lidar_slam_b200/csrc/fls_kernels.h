@@ -41,6 +41,7 @@ struct P2PlaneLoopArgs {
     int log_cap;
     const P2PlaneScan* scans;  // [n_scans]; every CTA serves every scan, CTA (s mod grid) folds and solves scan s
     int n_scans;
+    int visit_group;  // scans per visit (1..8): a warp works through its chunk of each of them between two CTA barriers
 };
 int p2plane_block();                   // threads per CTA of the selected kernel shape
 int p2plane_max_grid(int device);      // co-resident CTAs

@@ -205,7 +205,7 @@ __device__ __forceinline__ bool p2plane_point(const IvoxView& map, const float4 
 // columns of the per-point staging record
 constexpr int kRecAd = 6, kRecValid = 7, kRecCand = 8, kRecHits = 9, kRecOne = 10, kRecW = 12;
 
-constexpr int kVisitGroup = 4;  // scans whose chunks a warp works through between two CTA barriers
+constexpr int kVisitGroup = 8;  // most scans whose chunks a warp works through between two CTA barriers
 
 template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs a) {
@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
     constexpr int V = kVisitGroup < W ? kVisitGroup : W;
     extern __shared__ __align__(16) unsigned char s_dyn[];
     double (*s_rec)[32][kRecW] = reinterpret_cast<double (*)[32][kRecW]>(s_dyn);  // [W][32][kRecW] per-lane staging records
+    double (*s_part)[W][32] = reinterpret_cast<double (*)[W][32]>(s_dyn + sizeof(double) * W * 32 * kRecW);  // [V][W][32] per scan of the group: every warp's 32 sums
     __shared__ double s_pose[V][12];
-    __shared__ double s_part[V][W][32];  // per scan of the group: every warp's 32 sums
     __shared__ double s_red[W][32];      // fold scratch of the folding CTA
     __shared__ int s_stop[V];
     __shared__ unsigned char s_iter[kMaxBatch];  // iterations this CTA has completed of every scan (255 = scan finished)
@@ -260,7 +260,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
     while (n_left > 0) {
         // ---- the group: the next (up to V) unfinished scans in round-robin order (uniform: s_iter is shared) -------------
         int gs[V], git[V], nv = 0;
-        for (int k = 0; k < a.n_scans && nv < V; ++k) {
+        const int vmax = a.visit_group < V ? a.visit_group : V;
+        for (int k = 0; k < a.n_scans && nv < vmax; ++k) {
             const int s = (next + k) % a.n_scans;
             const int it = s_iter[s];
             if (it == 255) continue;
@@ -631,7 +632,10 @@ template <int BLOCK>
 struct P2PlaneShape {
     static constexpr int kMinB = BLOCK >= 768 ? 1 : 768 / BLOCK;
     static const void* fn() { return (const void*)p2plane_gn_kernel<BLOCK, kMinB>; }
-    static size_t smem() { return (size_t)(BLOCK / 32) * 32 * kRecW * sizeof(double); }
+    static size_t smem() {
+        constexpr int W = BLOCK / 32, V = kVisitGroup < W ? kVisitGroup : W;
+        return (size_t)W * 32 * kRecW * sizeof(double) + (size_t)V * W * 32 * sizeof(double);
+    }
     static int max_grid(int sms) {
         int per_sm = 0;
         cudaFuncSetAttribute(fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
