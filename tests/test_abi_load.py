@@ -50,3 +50,41 @@ def test_error_strings_and_invalid_args():
     bad = _abi.default_config(_abi.FLS_P2PLANE_IVOX, max_iterations=2147483647)  # IntNaN sentinel upstream
     h = C.c_void_p()
     assert L.fls_create(C.byref(bad), C.byref(h)) == _abi.FLS_ERR_INVALID_ARG
+
+
+def test_all_five_plugins_validate_and_fail_loudly_without_a_device():
+    """Every method of the reference's factory is accepted by the validator; on a box without a GPU creation stops at
+    FLS_ERR_NO_DEVICE (there is no CPU fallback), never at FLS_ERR_UNSUPPORTED."""
+    L = _lib.lib()
+    if L.fls_device_count() > 0:
+        return  # covered by the -m gpu tests on a GPU box
+    for m in range(5):
+        h = C.c_void_p()
+        cfg = _abi.default_config(m)
+        assert L.fls_create(C.byref(cfg), C.byref(h)) == _abi.FLS_ERR_NO_DEVICE, m
+    # constructor-argument checks of the kd-tree plug-ins (the reference CHECK_NE()s them against its NaN sentinels)
+    h = C.c_void_p()
+    bad = _abi.default_config(_abi.FLS_LOAM_FULL, corner_local_map_size=0)
+    assert L.fls_create(C.byref(bad), C.byref(h)) == _abi.FLS_ERR_INVALID_ARG
+    bad = _abi.default_config(_abi.FLS_P2PLANE_KNN, map_cloud_filter_size=0.0)
+    assert L.fls_create(C.byref(bad), C.byref(h)) == _abi.FLS_ERR_INVALID_ARG
+    bad = _abi.default_config(_abi.FLS_NDT, max_iterations=300)  # iteration field of the hand-over tags is 8 bits
+    assert L.fls_create(C.byref(bad), C.byref(h)) == _abi.FLS_ERR_UNSUPPORTED
+
+
+def test_batch_and_projector_argument_checks():
+    L = _lib.lib()
+    assert L.fls_match_batch(None, 1, None, None, 16, None, None, None) == _abi.FLS_ERR_INVALID_ARG
+    assert L.fls_match_batch_device(None, 1, None, None, None, None, None) == _abi.FLS_ERR_INVALID_ARG
+    import numpy as np
+    raw = np.zeros((4, 4), np.float32)
+    ring = np.zeros(4, np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n_out = C.c_size_t(0)
+    # null outputs are rejected before any device work
+    rc = L.fls_project(0, vp(raw), vp(ring), C.c_size_t(4), C.c_size_t(16), 2, 8, C.c_float(0.78), C.c_float(1.0), C.c_float(50.0), None, None,
+                       None, None, None, C.byref(n_out))
+    assert rc == _abi.FLS_ERR_INVALID_ARG
+    rc = L.fls_project(0, vp(raw), vp(ring), C.c_size_t(4), C.c_size_t(12), 2, 8, C.c_float(0.78), C.c_float(1.0), C.c_float(50.0), vp(raw), vp(raw),
+                       vp(ring), vp(ring), vp(ring), C.byref(n_out))
+    assert rc == _abi.FLS_ERR_INVALID_ARG  # stride 12 is neither layout
