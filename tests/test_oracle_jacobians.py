@@ -208,3 +208,74 @@ def test_ivox_mapping_mode_insertion_rule_against_numpy(world, traj):
         expect += int(need)
     assert 0 < added < len(scan)
     assert added == expect
+
+
+def test_ndt_incremental_voxel_updates_against_python_restatement(world, traj):
+    """IncrementalNDT::AddCloudToLocalMap + UpdateVoxel in mapping mode (incremental_ndt.h:130-227) restated in Python:
+    first-scan estimate of every voxel, then per voxel: pending points are consumed only when MORE than min_points are
+    waiting — first estimate, or running merge + eigenvalue clamp of the information matrix — and a voxel freezes once it
+    has absorbed more than max_points.  Compared voxel by voxel with the oracle after a stream of overlapping scans."""
+    cfg = default_config(FLS_NDT, localization_mode=0, ndt_min_points_in_voxel=5, ndt_max_points_in_voxel=50, ndt_capacity=1000000)
+    o = orc.Registration(cfg)
+    leaf, inv = cfg.source_cloud_filter_size, 1.0 / cfg.ndt_voxel_size
+    vox, first = {}, True
+    for k in range(6):
+        cloud = synth.make_scan(world, traj[k // 2], "vlp16", seed=500 + k)["points"]
+        T = traj[k // 2]
+        cloud[:, :3] = (cloud[:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+        o.add_cloud(cloud)
+        active = []
+        for p in orc.voxel_grid(cloud, leaf)[:, :3].astype(np.float64):
+            key = tuple((p * inv).astype(np.int32))  # C truncation [quirk 5]
+            v = vox.get(key)
+            if v is None:
+                vox[key] = dict(pts=[p], mu=np.zeros(3), sigma=np.zeros((3, 3)), info=np.zeros((3, 3)), est=False, n=1)
+            else:
+                v["pts"].append(p)
+                if not v["est"]:
+                    v["n"] += 1
+            if key not in active:
+                active.append(key)
+        for key in set(active):
+            v = vox[key]
+            P = np.array(v["pts"])
+            if first:
+                if len(P) > 1:
+                    v["mu"], v["sigma"] = P.mean(0), np.cov(P.T, ddof=1).reshape(3, 3)
+                    v["info"] = np.linalg.inv(v["sigma"] + 1e-3 * np.eye(3))
+                else:
+                    v["mu"], v["info"] = P[0], 100.0 * np.eye(3)
+                v["est"], v["pts"] = True, []
+                continue
+            if v["est"] and v["n"] > cfg.ndt_max_points_in_voxel:
+                continue
+            if len(P) > cfg.ndt_min_points_in_voxel:
+                cm, cv = P.mean(0), np.cov(P.T, ddof=1).reshape(3, 3)
+                if not v["est"]:
+                    v["mu"], v["sigma"] = cm, cv
+                    v["info"] = np.linalg.inv(cv + 1e-3 * np.eye(3))
+                    v["est"] = True
+                else:
+                    m, c = v["n"], len(P)
+                    nm = (m * v["mu"] + c * cm) / (m + c)
+                    nv = (m * (v["sigma"] + np.outer(v["mu"] - nm, v["mu"] - nm)) + c * (cv + np.outer(cm - nm, cm - nm))) / (m + c)
+                    v["mu"], v["sigma"], v["n"] = nm, nv, m + c
+                    lam, V = np.linalg.eigh(nv)
+                    lam, V = lam[::-1].copy(), V[:, ::-1]
+                    lam[1] = max(lam[1], lam[0] * 1e-3)
+                    lam[2] = max(lam[2], lam[0] * 1e-3)
+                    v["info"] = V @ np.diag(1.0 / lam) @ V.T
+                v["pts"] = []
+        first = False
+    keys, mu, info, est = o.ndt_dump()
+    assert len(keys) == len(vox)
+    n_est = n_merged = 0
+    for kk, m_, i_, e_ in zip(keys, mu, info, est):
+        v = vox[tuple(kk)]
+        assert bool(e_) == v["est"], kk
+        if v["est"]:
+            n_est += 1
+            n_merged += v["n"] > 10
+            assert np.allclose(m_, v["mu"], atol=1e-9), kk
+            assert np.allclose(i_, v["info"], rtol=1e-6, atol=1e-6 * np.abs(v["info"]).max()), kk
+    assert n_est > 500 and n_merged > 50 and n_est < len(vox)  # all three voxel states occur
