@@ -279,3 +279,75 @@ def test_ndt_incremental_voxel_updates_against_python_restatement(world, traj):
             assert np.allclose(m_, v["mu"], atol=1e-9), kk
             assert np.allclose(i_, v["info"], rtol=1e-6, atol=1e-6 * np.abs(v["info"]).max()), kk
     assert n_est > 500 and n_merged > 50 and n_est < len(vox)  # all three voxel states occur
+
+
+def test_icp_first_iteration_against_numpy(scene16):
+    """IcpOptimized::Match, iteration 0 (icp_optimized.h:57-127): VoxelGrid(source), fp32 transform with R, t cast to float,
+    exact 1-NN on VoxelGrid(map), gate d^2 > max_correspond_distance [quirk 4], J = [I | -R p^], serial sums."""
+    from scipy.spatial import cKDTree
+    cfg = default_config(FLS_ICP_P2P, flags=FLS_FLAG_ITER_LOG, max_iterations=1)
+    r = orc.Registration(cfg)
+    r.add_cloud(scene16["map"])
+    T = scene16["guess"]
+    r.match(scene16["scan"], T)
+    lg = r.iter_log()[0]
+    src = orc.voxel_grid(scene16["scan"], cfg.source_cloud_filter_size)[:, :3]
+    mp = orc.voxel_grid(scene16["map"], cfg.map_cloud_filter_size)[:, :3]
+    Rf, tf = T[:3, :3].astype(np.float32), T[:3, 3].astype(np.float32)
+    # q = R_f p + t_f in fp32, row by row in the order ((r0 x + r1 y) + r2 z) + t
+    q = ((Rf[None, :, 0] * src[:, None, 0] + Rf[None, :, 1] * src[:, None, 1]) + Rf[None, :, 2] * src[:, None, 2]) + tf[None, :]
+    assert q.dtype == np.float32
+    tree = cKDTree(mp.astype(np.float64))
+    _, nn = tree.query(q.astype(np.float64), k=1)
+    d = q - mp[nn]
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]  # fp32 squared distance, as FLANN returns it
+    keep = ~(d2.astype(np.float64) > cfg.icp_max_correspond_distance)
+    H, g, res = np.zeros((6, 6)), np.zeros(6), 0.0
+    R = T[:3, :3]
+    for i in np.where(keep)[0]:
+        e = q[i].astype(np.float64) - mp[nn[i]].astype(np.float64)
+        J = np.hstack([np.eye(3), -R @ _hat(src[i].astype(np.float64))])
+        H += J.T @ J
+        g += -J.T @ e
+        res += np.linalg.norm(e)
+    assert int(keep.sum()) == lg["n_valid"] and lg["n_valid"] > 1000
+    assert np.allclose(H, lg["H"], rtol=1e-9, atol=1e-9 * np.abs(H).max())
+    assert np.allclose(g, lg["g"], rtol=1e-9, atol=1e-7)
+    assert res == pytest.approx(lg["sum_residual"], rel=1e-9)
+
+
+def test_ndt_first_iteration_against_numpy(scene16):
+    """IncrementalNDT::Match, iteration 0 (incremental_ndt.h:232-304): VoxelGrid(source), fp64 q = R p + t, C-truncated key,
+    7 stencil probes, chi-square gate, J = [-R p^ | I], H += J^T L J, err -= J^T L e, effective = number of accepted
+    (point, voxel) pairs."""
+    cfg = default_config(FLS_NDT, flags=FLS_FLAG_ITER_LOG, max_iterations=1)
+    r = orc.Registration(cfg)
+    r.add_cloud(scene16["map"])
+    keys, mu, info, est = r.ndt_dump()
+    lut = {tuple(k): i for i, k in enumerate(keys)}
+    T = scene16["guess_small"]
+    r.match(scene16["scan"], T)
+    lg = r.iter_log()[0]
+    src = orc.voxel_grid(scene16["scan"], cfg.source_cloud_filter_size)[:, :3].astype(np.float64)
+    R, t = T[:3, :3], T[:3, 3]
+    stencil = [(0, 0, 0), (-1, 0, 0), (1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, -1), (0, 0, 1)]
+    H, g, n_eff, chi_sum = np.zeros((6, 6)), np.zeros(6), 0, 0.0
+    for p in src:
+        q = R @ p + t
+        k0 = (q * (1.0 / cfg.ndt_voxel_size)).astype(np.int32)
+        J = np.hstack([-R @ _hat(p), np.eye(3)])
+        for o in stencil:
+            vi = lut.get((k0[0] + o[0], k0[1] + o[1], k0[2] + o[2]))
+            if vi is None or not est[vi]:
+                continue
+            e = q - mu[vi]
+            chi = e @ info[vi] @ e
+            if np.isnan(chi) or chi > cfg.ndt_outlier_thres:
+                continue
+            H += J.T @ info[vi] @ J
+            g += -J.T @ info[vi] @ e
+            n_eff += 1
+            chi_sum += chi
+    assert n_eff == lg["n_valid"] and n_eff > 1000
+    assert np.allclose(H, lg["H"], rtol=1e-8, atol=1e-9 * np.abs(H).max())
+    assert np.allclose(g, lg["g"], rtol=1e-8, atol=1e-6)
