@@ -88,3 +88,27 @@ def test_batch_and_projector_argument_checks():
     rc = L.fls_project(0, vp(raw), vp(ring), C.c_size_t(4), C.c_size_t(12), 2, 8, C.c_float(0.78), C.c_float(1.0), C.c_float(50.0), vp(raw), vp(raw),
                        vp(ring), vp(ring), vp(ring), C.byref(n_out))
     assert rc == _abi.FLS_ERR_INVALID_ARG  # stride 12 is neither layout
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/fls_b200.h must compile as C99 (the boundary is a C ABI) and gcc's struct layouts must be the ones the ctypes
+    mirror (and therefore the tests and the bench) assume."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        return
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "fls_b200.h"\n'
+        "int main(void) {\n"
+        '  printf("%zu %zu %zu %zu %zu ", sizeof(fls_config), sizeof(fls_match_stats), sizeof(fls_iter_log), sizeof(fls_map_info), sizeof(fls_feature_cfg));\n'
+        '  printf("%zu %zu %zu %zu\\n", offsetof(fls_config, point_to_planar_thres), offsetof(fls_config, ndt_voxel_size), offsetof(fls_config, point_search_thres), offsetof(fls_match_stats, algo_bytes));\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "abi"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(_abi.FlsConfig), C.sizeof(_abi.FlsMatchStats), C.sizeof(_abi.FlsIterLog), C.sizeof(_abi.FlsMapInfo), C.sizeof(_abi.FlsFeatureCfg),
+            _abi.FlsConfig.point_to_planar_thres.offset, _abi.FlsConfig.ndt_voxel_size.offset, _abi.FlsConfig.point_search_thres.offset,
+            _abi.FlsMatchStats.algo_bytes.offset]
+    assert got == want, (got, want)
