@@ -17,6 +17,8 @@
 #include <glog/logging.h>
 
 #include <limits>
+#include <memory>
+#include <string>
 #include <vector>
 
 #include "common/constant_variable.h"
