@@ -161,6 +161,7 @@ static GnLoopCtl make_ctl(Handle& h, int method, int grid, int min_effective) {
     c.gp.pos_thres = h.cfg.position_converge_thres;
     c.log = h.log.p;
     c.log_cap = h.log_cap;
+    c.result = h.result_buf;
     return c;
 }
 
@@ -243,6 +244,7 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
         d.rows = ll_rows.p + (size_t)s * grid * 32;
         d.ll_pose = pose_base + (size_t)s * kLlPoseLen;
         d.log = log_cap ? log.p + (size_t)s * log_cap : nullptr;
+        d.result = (result_buf && (size_t)s < result_cap) ? result_buf + (size_t)s * kResultLen : nullptr;
     }
     ho[B] = off[B];
     FLS_CUDA(cudaMemcpyAsync(d_batch.p, h_batch, tbl_bytes, cudaMemcpyHostToDevice, stream));
@@ -1041,6 +1043,14 @@ int fls_fitness(fls_handle* hh, float max_range, float* score) {
     FLS_TRY
     return h->fitness(max_range, score);
     FLS_CATCH
+}
+
+int fls_set_result_buffer_device(fls_handle* hh, double* d_results, size_t capacity_scans) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || (d_results && capacity_scans == 0)) return FLS_ERR_INVALID_ARG;
+    h->result_buf = d_results;
+    h->result_cap = d_results ? capacity_scans : 0;
+    return FLS_OK;
 }
 
 int fls_get_iter_log(const fls_handle* hh, fls_iter_log* out, int capacity) {

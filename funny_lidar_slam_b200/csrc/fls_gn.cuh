@@ -29,7 +29,9 @@ struct GnLoopCtl {
     GnParams gp;
     fls_iter_log* log;
     int log_cap;
+    double* result;  // optional device buffer of kResultLen doubles, written when the loop stops (fls_set_result_buffer_device)
 };
+static constexpr int kResultLen = 18;  // column-major 4x4 pose, converged, iterations
 
 void launch_gn_init(GnState* d_state, const double* T_colmajor, cudaStream_t st);
 
@@ -74,7 +76,7 @@ __device__ __forceinline__ void gn_load(const GnState* s, GnPre& q) {
 // applies the plug-in's stop rule.  Executed by a single thread: the arithmetic runs on locals, what the other CTAs wait
 // for (pose + stop word, as LL records) goes out first and the bookkeeping follows.
 __device__ inline void gn_step_pre(GnState* s, const GnPre& q, const double* tot, const GnParams& p, fls_iter_log* log, int log_cap,
-                                   uint4* ll_pose, unsigned ll_tag) {
+                                   uint4* ll_pose, unsigned ll_tag, double* result = nullptr) {
     double R[9], t[3];
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = q.R[i];
@@ -154,6 +156,18 @@ __device__ inline void gn_step_pre(GnState* s, const GnPre& q, const double* tot
 #pragma unroll
     for (int i = 0; i < 3; ++i) s->t[i] = t[i];
     if (stop) s->done = 1;
+    if (stop && result) {  // packed result for a device-side consumer (the multi-GPU pose all-gather): Eigen Mat4d memory + flags
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            result[c * 4 + 0] = R[c];
+            result[c * 4 + 1] = R[3 + c];
+            result[c * 4 + 2] = R[6 + c];
+            result[c * 4 + 3] = 0.0;
+        }
+        result[12] = t[0]; result[13] = t[1]; result[14] = t[2]; result[15] = 1.0;
+        result[16] = converged > 0 ? 1.0 : 0.0;
+        result[17] = (double)(it + 1);
+    }
     // pose before the update (LOAM-iVox map insertion rule)
 #pragma unroll
     for (int i = 0; i < 9; ++i) s->Rprev[i] = q.R[i];
@@ -263,7 +277,7 @@ __device__ __forceinline__ bool gn_handover(double (&acc)[kNumAcc], const GnLoop
             __syncwarp();
             s_red[0][lane] = t;
             __syncwarp();
-            if (lane == 0) gn_step_pre(c.state, pre, s_red[0], c.gp, c.log, c.log_cap, c.ll_pose, tag);
+            if (lane == 0) gn_step_pre(c.state, pre, s_red[0], c.gp, c.log, c.log_cap, c.ll_pose, tag, c.result);
         }
     }
     if (threadIdx.x < 13) {

@@ -48,6 +48,10 @@ struct Handle {
     long long per_hit_bytes = 0;         // bytes per table probe that hit (NDT voxel record)
     BuildScratch scratch;                // voxel-grid passes of Match
 
+    // optional caller-owned device buffer that receives {pose, converged, iterations} per scan (fls_set_result_buffer_device)
+    double* result_buf = nullptr;
+    size_t result_cap = 0;
+
     // source cloud of the last Match (for GetFitnessScore): device pointer + count
     const float4* last_src = nullptr;
     size_t last_src_n = 0;

@@ -31,6 +31,7 @@ struct P2PlaneScan {
     uint4* rows;     // [grid][32] LL records {lo, tag, hi, tag}: one per CTA and sum
     uint4* ll_pose;  // [kLlPoseLen] LL records: next pose + stop word, published by the folding CTA
     fls_iter_log* log;
+    double* result;  // optional packed result (kResultLen doubles), written by the folder when the scan stops
 };
 
 // whole-loop arguments of the persistent LoamPointToPlaneIVOX kernel (K1 + fused K6); one launch = a batch of scans

@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) p2plane_gn_kernel(P2PlaneLoopArgs
                 __syncwarp();
                 if (lane == 0) {
                     if (it < 16) state->dbg[it][2] = globaltimer_ns();
-                    gn_step_pre(state, pre, s_red[0], a.gp, sc->log, a.log_cap, sc->ll_pose, tag);
+                    gn_step_pre(state, pre, s_red[0], a.gp, sc->log, a.log_cap, sc->ll_pose, tag, sc->result);
                     if (it < 16) state->dbg[it][3] = globaltimer_ns();
                 }
             }

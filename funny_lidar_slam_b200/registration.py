@@ -128,6 +128,11 @@ class Registration:
         self.last_stats = st[0]
         return np.array(conv[:], bool), np.transpose(Tc, (0, 2, 1)).copy()
 
+    def set_result_buffer_device(self, d_ptr: int, capacity_scans: int) -> None:
+        """Every later Match also writes {column-major pose, converged, iterations} (18 doubles per scan) to this device
+        buffer from inside the GN kernel — the input of the per-batch pose all-gather (parallel.py)."""
+        check(lib().fls_set_result_buffer_device(self._h, C.c_void_p(d_ptr) if d_ptr else None, int(capacity_scans)), "fls_set_result_buffer_device")
+
     # -- device-resident scan (bench `value` leg) ---------------------------------------------------------
     def match_device(self, d_ptr: int, n: int, T: np.ndarray) -> bool:
         Tc = np.ascontiguousarray(np.asarray(T, np.float64).T).copy()

@@ -130,7 +130,7 @@ typedef struct {
     float kernel_ms;      /* FLS_FLAG_PROFILE: summed device time of the residual kernel over the executed iterations */
     int32_t kernel_launches; /* FLS_FLAG_PROFILE: how many launches kernel_ms covers (= iterations) */
     int64_t algo_bytes;   /* FLS_FLAG_PROFILE: algorithmic bytes those launches moved (DESIGN.md "roofline accounting") */
-} fls_match_stats;
+} fls_match_stats;  /* valid only when the call returned FLS_OK */
 
 typedef struct {
     double H[36]; /* row-major 6x6 (symmetric) */
@@ -171,7 +171,6 @@ int fls_match_device(fls_handle* h, const void* d_points, size_t n, double T_col
 /* GetFitnessScore(max_range): FLT_MAX when unsupported / no inliers, as upstream. */
 int fls_fitness(fls_handle* h, float max_range, float* score);
 
-/* per-iteration log of the last fls_match (needs FLS_FLAG_ITER_LOG); returns the number of entries written */
 /* Batched Match for throughput (the benchmark entry SURVEY.md §8b names): `n_scans` (<= 64) independent scans, each with its
  * own in-out pose T[s*16 .. s*16+15], converged[s] and stats[s], matched against the same map in ONE persistent launch.
  * Implemented for FLS_P2PLANE_IVOX; more than one scan requires localization_mode (Match must not modify the map).
@@ -182,6 +181,14 @@ int fls_match_batch(fls_handle* h, int n_scans, const void* const* planar, const
 int fls_match_batch_device(fls_handle* h, int n_scans, const void* const* d_planar, const size_t* n, double* T_colmajor, int* converged,
                            fls_match_stats* stats);
 
+/* Device-side results for a consumer that lives on the GPU (the per-batch NCCL all-gather of poses): once set,
+ * every Match additionally writes, for scan s of the call, 18 doubles at d_results + 18*s — the column-major Mat4d pose
+ * (what T receives), converged (0/1), iterations — from inside the Gauss-Newton kernel when the scan stops; the buffer is
+ * complete when the Match call returns.  `capacity_scans` bounds s; NULL unsets.  The buffer is owned by the caller and must
+ * stay valid until unset or the handle is destroyed. */
+int fls_set_result_buffer_device(fls_handle* h, double* d_results, size_t capacity_scans);
+
+/* per-iteration log of the last fls_match (needs FLS_FLAG_ITER_LOG; batch: scan 0); returns the number of entries written */
 int fls_get_iter_log(const fls_handle* h, fls_iter_log* out, int capacity);
 
 int fls_get_map_info(const fls_handle* h, fls_map_info* out);

@@ -78,3 +78,55 @@ def test_two_rank_gloo_batch(tmp_path):
         T, ok, it = parallel.unpack_result(r0[i])
         assert ok and it >= 1
         assert synth.pose_error(T, traj[i])[0] < 0.05  # scan i really is at slot i
+
+
+def _async_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 3
+    g = parallel.AsyncResultGather(n, device=None, depth=2)
+    got = []
+    for step in range(5):
+        buf = g.begin_step()  # what the GN kernel writes on the GPU box; here the test fills it
+        vals = torch.arange(n * parallel.RESULT_LEN, dtype=torch.float64) + 1000.0 * rank + 100000.0 * step
+        buf.copy_(vals)
+        g.launch()
+        prev = g.take_previous()
+        assert (prev is None) == (step == 0)  # one step deferred
+        if prev is not None:
+            got.append(prev)
+    got += g.drain()
+    assert len(got) == 5 and g.drain() == []
+    np.save(os.path.join(out_dir, f"async{rank}.npy"), np.stack(got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_async_result_gather_two_ranks(tmp_path):
+    """The deferred device-buffer all-gather bench.py runs per step (NCCL there, gloo here): step k's results come out at
+    step k+1, every rank sees every rank's buffer, buffers rotate without being overwritten early."""
+    import torch.multiprocessing as mp
+
+    world = 2
+    mp.spawn(_async_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a0, a1 = np.load(tmp_path / "async0.npy"), np.load(tmp_path / "async1.npy")
+    assert a0.shape == (5, world, 3, parallel.RESULT_LEN) and np.array_equal(a0, a1)
+    base = np.arange(3 * parallel.RESULT_LEN, dtype=np.float64).reshape(3, parallel.RESULT_LEN)
+    for step in range(5):
+        for r in range(world):
+            assert np.array_equal(a0[step, r], base + 1000.0 * r + 100000.0 * step)
+
+
+def test_async_result_gather_single_process_identity():
+    import torch
+    g = parallel.AsyncResultGather(2)
+    b = g.begin_step()
+    b.copy_(torch.arange(2 * parallel.RESULT_LEN, dtype=torch.float64))
+    g.launch()
+    assert g.take_previous() is None
+    (out,) = g.drain()
+    assert out.shape == (1, 2, parallel.RESULT_LEN) and out[0, 1, 0] == parallel.RESULT_LEN
