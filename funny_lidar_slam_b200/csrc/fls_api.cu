@@ -185,10 +185,11 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
     int off[kMaxBatch + 1];
     off[0] = 0;
     int grid = 1;
+    const bool use_v9 = !(std::getenv("FLS_K1") && std::atoi(std::getenv("FLS_K1")) == 8);
     for (int s = 0; s < B; ++s) {
         if (n[s] > 0x3fffffffull || (long long)off[s] + (long long)n[s] > 0x7ffffff0ll) return FLS_ERR_INVALID_ARG;
         off[s + 1] = off[s] + (int)n[s];
-        const int g = p2plane_grid((int)n[s], cfg.device);
+        const int g = use_v9 ? p2plane_v9_grid((int)n[s], cfg.device) : p2plane_grid((int)n[s], cfg.device);
         if (g > grid) grid = g;
     }
     const int n_total = off[B];
@@ -203,7 +204,7 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
     // is ever cleared — only zeroed when (re)allocated, so that uninitialised memory cannot alias a tag
     {
         const size_t cap0 = ll_rows.cap;
-        ll_rows.reserve((size_t)B * grid * 32 + (size_t)B * kLlPoseLen);
+        ll_rows.reserve((size_t)B * grid * 32 + (size_t)B * kLlPoseLen + (size_t)B * 16 * 32);
         if (ll_rows.cap != cap0) FLS_CUDA(cudaMemsetAsync(ll_rows.p, 0, ll_rows.cap * sizeof(uint4), stream));
     }
     match_epoch = (match_epoch + 1) & 0xffffffu;
@@ -245,6 +246,7 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
         d.ll_pose = pose_base + (size_t)s * kLlPoseLen;
         d.log = log_cap ? log.p + (size_t)s * log_cap : nullptr;
         d.result = (result_buf && (size_t)s < result_cap) ? result_buf + (size_t)s * kResultLen : nullptr;
+        d.grows = pose_base + (size_t)B * kLlPoseLen + (size_t)s * 16 * 32;
     }
     ho[B] = off[B];
     FLS_CUDA(cudaMemcpyAsync(d_batch.p, h_batch, tbl_bytes, cudaMemcpyHostToDevice, stream));
@@ -272,6 +274,10 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
         const char* e = std::getenv("FLS_VISIT_GROUP");
         const int v = e ? std::atoi(e) : 8;  // measured at batch 8: group 2 / 3 / 4 / 6 / 8 -> 783 / 734 / 703 / 724 / 687 us per launch
         a.visit_group = v < 1 ? 1 : (v > 8 ? 8 : v);
+        if (use_v9) {  // v9: the field carries experiment switches (FLS_K1_OPTS bit 0: single selection chain)
+            const char* o = std::getenv("FLS_K1_OPTS");
+            a.visit_group = o ? std::atoi(o) : 0;
+        }
     }
     // roofline accounting (SURVEY.md §8d, K1 — the REFERENCE algorithm's traffic): 16 B source point + n_stencil x 16 B
     // slot probes + 32 B persistent record per point-iteration, 16 B per map record resident in the stencil voxels.
@@ -279,7 +285,16 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
     per_cand_bytes = 16;
     per_hit_bytes = 0;
     if (profile) FLS_CUDA(cudaEventRecord(prof_ev[0], stream));
-    launch_p2plane_loop(a, grid, stream);
+    a.tickets = nullptr;
+    a.ticket_stride = 0;
+    if (use_v9) {  // chunk tickets of the dynamic work distribution: one counter per (scan, iteration)
+        a.ticket_stride = cfg.max_iterations + 2;
+        tickets.reserve((size_t)B * a.ticket_stride);
+        FLS_CUDA(cudaMemsetAsync(tickets.p, 0, sizeof(unsigned) * (size_t)B * a.ticket_stride, stream));
+        a.tickets = tickets.p;
+    }
+    if (use_v9) launch_p2plane_v9(a, grid, stream);
+    else launch_p2plane_loop(a, grid, stream);
     if (profile) FLS_CUDA(cudaEventRecord(prof_ev[1], stream));
     launches++;
     fused_loop = true;
@@ -328,11 +343,26 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
         const GnState& g0 = h_state[0];
         std::fprintf(stderr, "[fls timing] batch %d  scan 0: iters %d  candidates/pt-iter %.1f\n", B, g0.iter,
                      g0.cand_total / (double)((long long)n[0] * (g0.iter > 0 ? g0.iter : 1)));
+        if (use_v9 && std::getenv("FLS_K1_TRACE")) {
+            const unsigned long long* c = &g0.dbg[8][0];
+            std::fprintf(stderr, "[fls trace] warp-time us: wait %.0f prefetch %.0f compute %.0f - %.0f | chunks %llu mean compute %.2f us max %.1f us | mixed chunks %llu exact lanes %llu\n",
+                         c[0] * 1e-3, c[1] * 1e-3, c[2] * 1e-3, c[3] * 1e-3, c[5], c[5] ? c[2] * 1e-3 / c[5] : 0.0, c[4] * 1e-3, c[6], c[7]);
+        }
+        if (use_v9 && std::getenv("FLS_K1_TRACE"))
+            for (int it = 0; it < g0.iter && it < 4; ++it)
+                std::fprintf(stderr, "[fls trace] it %d: row(cta0)->last row out %.1f us | last row out->folder has all %.1f us | fold trips %llu, first take %.1f us and half %.1f us before the end\n", it,
+                             ((double)g0.dbg[10 + it][0] - (double)g0.dbg[it][2]) * 1e-3, ((double)g0.dbg[it][3] - (double)g0.dbg[10 + it][0]) * 1e-3,
+                             g0.dbg[10 + it][1], ((double)g0.dbg[it][3] - (double)g0.dbg[10 + it][2]) * 1e-3, ((double)g0.dbg[it][3] - (double)g0.dbg[10 + it][3]) * 1e-3);
         for (int it = 0; it < g0.iter && it < 16; ++it) {
             const unsigned long long* d = g0.dbg[it];
-            std::fprintf(stderr, "[fls timing] it %d: until all rows in %.1f us | fold %.1f us | solve+publish %.1f us | to next start %.1f us\n", it,
-                         (d[1] - d[0]) * 1e-3, (d[2] - d[1]) * 1e-3, (d[3] - d[2]) * 1e-3,
-                         (it + 1 < g0.iter && it + 1 < 16) ? (g0.dbg[it + 1][0] - d[3]) * 1e-3 : 0.0);
+            if (use_v9)  // [0] item opened on CTA 0, [1] CTA 0 saw the tickets exhausted, [2] CTA 0's row out, [3] folder has all rows
+                std::fprintf(stderr, "[fls timing] it %d: open->exhausted %.1f us | exhausted->row(cta0) %.1f us | row(cta0)->all rows %.1f us | all rows->next open %.1f us\n", it,
+                             (d[1] - d[0]) * 1e-3, ((double)d[2] - (double)d[1]) * 1e-3, ((double)d[3] - (double)d[2]) * 1e-3,
+                             (it + 1 < g0.iter && it + 1 < 16) ? ((double)g0.dbg[it + 1][0] - (double)d[3]) * 1e-3 : 0.0);
+            else
+                std::fprintf(stderr, "[fls timing] it %d: until all rows in %.1f us | fold %.1f us | solve+publish %.1f us | to next start %.1f us\n", it,
+                             (d[1] - d[0]) * 1e-3, (d[2] - d[1]) * 1e-3, (d[3] - d[2]) * 1e-3,
+                             (it + 1 < g0.iter && it + 1 < 16) ? (g0.dbg[it + 1][0] - d[3]) * 1e-3 : 0.0);
         }
     }
     return FLS_OK;

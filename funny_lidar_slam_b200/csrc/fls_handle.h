@@ -28,6 +28,7 @@ struct Handle {
     DevBuf<float4> stage2;      // transformed / filtered intermediates
     DevBuf<float4> rec0, rec1;  // persistent per-point {J, |d|} records (LOAM plug-ins)
     DevBuf<unsigned char> flags;
+    DevBuf<unsigned> tickets;   // chunk ticket counters of the LOAM-iVox kernel (dynamic work distribution)
     DevBuf<uint4> ll_rows;      // LL hand-over records of the persistent LOAM-iVox kernel: [grid][32] rows + pose record
     unsigned match_epoch = 0;   // tag prefix of those records
     unsigned char* h_batch = nullptr;  // pinned staging of the per-batch tables (poses, offsets, scan descriptors, CTA map, pointers)

@@ -32,6 +32,7 @@ struct P2PlaneScan {
     uint4* ll_pose;  // [kLlPoseLen] LL records: next pose + stop word, published by the folding CTA
     fls_iter_log* log;
     double* result;  // optional packed result (kResultLen doubles), written by the folder when the scan stops
+    uint4* grows;    // v9: [16][32] LL records: group rows of the two-level fold
 };
 
 // whole-loop arguments of the persistent LoamPointToPlaneIVOX kernel (K1 + fused K6); one launch = a batch of scans
@@ -43,12 +44,17 @@ struct P2PlaneLoopArgs {
     const P2PlaneScan* scans;  // [n_scans]; every CTA serves every scan, CTA (s mod grid) folds and solves scan s
     int n_scans;
     int visit_group;  // scans per visit (1..8): a warp works through its chunk of each of them between two CTA barriers
+    unsigned* tickets;  // v9: chunk ticket counters [n_scans][ticket_stride], zeroed before the launch
+    int ticket_stride;  // >= max_iterations + 2
 };
 int p2plane_block();                   // threads per CTA of the selected kernel shape
 int p2plane_max_grid(int device);      // co-resident CTAs
 int p2plane_chunks(int n);             // warp-sized (32-point) work chunks
 int p2plane_grid(int n, int device);    // CTAs that serve a scan of n points: its chunks / warps per CTA, + the folder, <= co-resident
 void launch_p2plane_loop(const P2PlaneLoopArgs& a, int grid, cudaStream_t st);
+// generation 9 of the same loop (fls_p2plane_v9.cu): barrier-free dataflow, TMA-staged candidate runs, DMMA sums
+int p2plane_v9_grid(int n_max, int device);
+void launch_p2plane_v9(const P2PlaneLoopArgs& a, int grid, cudaStream_t st);
 // d_scan_ptrs[n_scans]: device pointers of the scans; d_offsets[n_scans + 1]: their positions in the batch; d_poses / d_states[n_scans]
 void prepare_queries(const float4* const* d_scan_ptrs, int n_total, const int* d_offsets, int n_scans, const PoseArg* d_poses, GnState* d_states,
                      const IvoxView& map, unsigned char* d_flags, float4* d_sorted, BuildScratch& sc, cudaStream_t st, int* launches);

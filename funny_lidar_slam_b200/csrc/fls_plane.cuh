@@ -146,14 +146,23 @@ __device__ __forceinline__ void plane_lstsq(double (&A)[5][3], double (&c)[3]) {
     c[2] = (p0 == 2) ? y0 : ((p1 == 2) ? y1 : y2);
 }
 
+// neighbour fetch: read-only global path (kLdg) or a generic load (the point may sit in shared memory: K1 stages the
+// candidate runs of a chunk there with cp.async.bulk, fls_p2plane.cu)
+template <bool kLdg>
+__device__ __forceinline__ float4 plane_ld(const float4* p) {
+    if (kLdg) return __ldg(p);
+    return *p;
+}
+
 // Out-of-line QR path for ill-conditioned neighbourhoods (kept out of the hot path's register budget).
-__device__ __noinline__ void plane_lstsq_qr(const float4* __restrict__ lists, unsigned j0, unsigned j1, unsigned j2, unsigned j3, unsigned j4,
+template <bool kLdg>
+__device__ __noinline__ void plane_lstsq_qr(const float4* lists, unsigned j0, unsigned j1, unsigned j2, unsigned j3, unsigned j4,
                                             double (&c)[3]) {
     const unsigned js[5] = {j0, j1, j2, j3, j4};
     double A[5][3];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        const float4 a = __ldg(lists + js[i]);
+        const float4 a = plane_ld<kLdg>(lists + js[i]);
         A[i][0] = a.x; A[i][1] = a.y; A[i][2] = a.z;
     }
     plane_lstsq(A, c);
@@ -161,7 +170,8 @@ __device__ __noinline__ void plane_lstsq_qr(const float4* __restrict__ lists, un
 
 // Plane through the 5 neighbours P[js[0..4]] (js[0] = nearest) -> J (6) and |d| of source point `sp` whose transformed
 // position is q.  Returns false when upstream rejects the point (invalid plane, near-point gate).
-__device__ __forceinline__ bool plane_term(const float4* __restrict__ P, const unsigned (&js)[5], const float4 sp, float qx, float qy, float qz,
+template <bool kLdg = true>
+__device__ __forceinline__ bool plane_term(const float4* P, const unsigned (&js)[5], const float4 sp, float qx, float qy, float qz,
                                            const double* __restrict__ pose /*R[9], t[3]*/, double plane_thres, double (&J)[6], double& ad,
                                            unsigned& n_fallback) {
     double c[3];
@@ -172,7 +182,7 @@ __device__ __forceinline__ bool plane_term(const float4* __restrict__ P, const u
         double sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0, bx = 0, by = 0, bz = 0;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            const float4 a = __ldg(P + js[i]);
+            const float4 a = plane_ld<kLdg>(P + js[i]);
             const double x = a.x, y = a.y, z = a.z;
             sxx += x * x; sxy += x * y; sxz += x * z; syy += y * y; syz += y * z; szz += z * z;
             bx -= x; by -= y; bz -= z;
@@ -198,7 +208,7 @@ __device__ __forceinline__ bool plane_term(const float4* __restrict__ P, const u
             c[2] = c2;
         } else {
             ++n_fallback;
-            plane_lstsq_qr(P, js[0], js[1], js[2], js[3], js[4], c);
+            plane_lstsq_qr<kLdg>(P, js[0], js[1], js[2], js[3], js[4], c);
         }
     }
     const double cn = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
@@ -209,7 +219,7 @@ __device__ __forceinline__ bool plane_term(const float4* __restrict__ P, const u
     float4 a0 = make_float4(0, 0, 0, 0);
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        const float4 a = __ldg(P + js[i]);
+        const float4 a = plane_ld<kLdg>(P + js[i]);
         if (i == 0) a0 = a;
         if (fabs((double)a.x * c[0] + (double)a.y * c[1] + (double)a.z * c[2] + 1.0) > lim) valid = false;
     }

@@ -15,7 +15,7 @@ from funny_lidar_slam_b200 import _abi  # noqa: E402
 from funny_lidar_slam_b200.registration import Registration  # noqa: E402
 
 wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "p2plane_ivox_64"]
-mp, scans, truths, guesses = bench.build_scene(wl, 0, 4, lambda m: None)
+mp, scans, truths, guesses = bench.build_scene(wl, 4, lambda m: None)
 reg = Registration(bench.make_cfg(wl, 0, len(mp), flags=_abi.FLS_FLAG_PROFILE))
 reg.AddCloudToLocalMap([mp])
 d = [torch.from_numpy(s).cuda() for s in scans]
