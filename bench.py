@@ -435,7 +435,7 @@ def main():
     n_pool = max(16, 2 * B)
     mp, scans, truths, guesses = build_scene(wl, n_pool, log)
     cfg = make_cfg(wl, local_rank, len(mp))
-    batched = wl["method"] == _abi.FLS_P2PLANE_IVOX  # plug-ins with a batch entry (fls_match_batch)
+    batched = wl["method"] in (_abi.FLS_P2PLANE_IVOX, _abi.FLS_NDT)  # plug-ins with a batch entry (fls_match_batch)
     reg = Registration(cfg)
     reg.AddCloudToLocalMap([mp])
     mi = reg.map_info()
@@ -626,8 +626,8 @@ def main():
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "launches": int(k_launch), "avg_launch_us": launch_us, "algo_bytes_per_launch": k_bytes / max(k_launch, 1)}
         if wl["method"] == _abi.FLS_P2PLANE_IVOX:
-            roof["kernel"] = ("p2plane_gn_kernel (whole GN loop fused: iVox 5-NN + plane fit + J/r + 6x6 reduction + solve; one launch = every "
-                              "iteration of every scan of the batch)")
+            roof["kernel"] = ("p2plane_v9_kernel (whole GN loop fused: TMA-staged iVox 5-NN + plane fit + J/r + DMMA 6x6 reduction + solve; one "
+                              "launch = every iteration of every scan of the batch)")
             if prof:
                 # second roofline: what the kernel is really bound by.  Static inputs from the committed ncu
                 # capture of the shipped configuration (profiles/traffic_k1.json), times measured live above.
@@ -639,7 +639,8 @@ def main():
                     roof["dram_frac"] = traffic / (launch_us * 1e-6) / 1e9 / peak
                 roof["traffic_source"] = prof.get("source")
         else:
-            roof["kernel"] = "ndt_gn_kernel (whole GN loop fused: 7-probe NDT residual + 6x6 reduction + solve)"
+            roof["kernel"] = ("ndt_gn_batch_kernel (one cooperative launch per batch: a sub-grid and a fused GN loop per scan — 7-probe NDT "
+                              "residual + 6x6 reduction + solve)")
         out = {
             "metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

@@ -15,7 +15,7 @@ EXPORTS = [
     "fls_abi_version", "fls_device_count", "fls_last_error", "fls_strerror", "fls_config_default", "fls_create", "fls_destroy",
     "fls_add_cloud", "fls_match", "fls_match_device", "fls_fitness", "fls_get_iter_log", "fls_get_map_info", "fls_ivox_knn",
     "fls_voxel_grid", "fls_extract_features", "fls_project", "fls_match_batch", "fls_match_batch_device",
-    "fls_set_result_buffer_device",
+    "fls_set_result_buffer_device", "fls_get_voxel_keys", "fls_get_map_points", "fls_ivox_add_points",
 ]
 
 
@@ -55,7 +55,10 @@ def lib():
     L.fls_fitness.argtypes = [vp, f32, C.POINTER(f32)]
     L.fls_get_iter_log.argtypes = [vp, C.POINTER(FlsIterLog), C.c_int]
     L.fls_get_map_info.argtypes = [vp, C.POINTER(FlsMapInfo)]
+    L.fls_get_voxel_keys.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.fls_get_map_points.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.fls_ivox_knn.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp]
+    L.fls_ivox_add_points.argtypes = [vp, vp, sz, sz]
     L.fls_voxel_grid.argtypes = [C.c_int, vp, sz, sz, f32, vp, C.POINTER(sz)]
     L.fls_extract_features.argtypes = [C.POINTER(FlsFeatureCfg), vp, vp, sz, vp, vp, i32, vp, C.POINTER(sz), vp, C.POINTER(sz),
                                        C.POINTER(FlsMatchStats)]

@@ -185,7 +185,12 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
     int off[kMaxBatch + 1];
     off[0] = 0;
     int grid = 1;
-    const bool use_v9 = !(std::getenv("FLS_K1") && std::atoi(std::getenv("FLS_K1")) == 8);
+    // K1 generations: the dataflow kernel (v9: TMA-staged runs, work ring, DMMA sums — fls_p2plane_v9.cu) serves batches; a single
+    // Match runs on the barrier kernel (v8, fls_p2plane.cu) whose one-chunk-per-warp round has the shorter hand-over (measured on
+    // B200, 108 k points: 139 vs 191 us per Match kernel; batch of 8: 683 vs 609 us).  FLS_K1=8 / 9 forces one of them.
+    const char* k1 = std::getenv("FLS_K1");
+    const int k1v = k1 ? std::atoi(k1) : 0;
+    const bool use_v9 = k1v == 9 || (k1v != 8 && B > 1);
     for (int s = 0; s < B; ++s) {
         if (n[s] > 0x3fffffffull || (long long)off[s] + (long long)n[s] > 0x7ffffff0ll) return FLS_ERR_INVALID_ARG;
         off[s + 1] = off[s] + (int)n[s];
@@ -448,6 +453,138 @@ int Handle::match_ndt(const float4* d_in, size_t n_in, double* T, int* converged
         if (st) st->gpu_launches = launches;
         if (rc2 != FLS_OK) return rc2;
     }
+    return FLS_OK;
+}
+
+// n_scans independent IncrementalNDT::Match calls against the same (static) map in ONE cooperative launch (fls_ndt.cu:
+// ndt_gn_batch_kernel — one sub-grid and one persistent Gauss-Newton loop per scan).  Localization semantics only: the map is
+// not modified (incremental_ndt.h:222-226, flag_first_scan_ stays set).
+int Handle::match_ndt_batch(int B, const float4* const* d_scans, const size_t* n_in, double* T, int* converged, fls_match_stats* st) {
+    if (ndt.n_vox == 0) return FLS_ERR_NO_MAP;
+    if (B < 1 || B > kMaxBatch) return FLS_ERR_INVALID_ARG;
+    size_t total_in = 0;
+    for (int s = 0; s < B; ++s) total_in += n_in[s];
+    src_f.reserve(total_in + 1);
+    state.reserve(kMaxBatch);
+    if (log_cap) log.reserve((size_t)log_cap * kMaxBatch);
+    // VoxelGridCloud of every source (incremental_ndt.h:232), back to back in one buffer
+    size_t off[kMaxBatch + 1];
+    off[0] = 0;
+    for (int s = 0; s < B; ++s) {
+        const size_t nf = voxel_grid_device(d_scans[s], n_in[s], cfg.source_cloud_filter_size, src_f.p + off[s], scratch, stream, &launches);
+        if (nf > 0x3fffffffull) return FLS_ERR_INVALID_ARG;
+        off[s + 1] = off[s] + nf;
+    }
+    // sub-grids: every scan gets the CTAs its points need, scaled down together when the device cannot hold them all
+    const int cap = ndt_max_grid(cfg.device);
+    int need[kMaxBatch], tot_need = 0;
+    for (int s = 0; s < B; ++s) {
+        need[s] = (int)((off[s + 1] - off[s] + kNdtBlock - 1) / kNdtBlock);
+        if (need[s] < 1) need[s] = 1;
+        tot_need += need[s];
+    }
+    if (B > cap) return FLS_ERR_INVALID_ARG;
+    int ncta[kMaxBatch], grid = 0;
+    for (int s = 0; s < B; ++s) {
+        ncta[s] = tot_need <= cap ? need[s] : (int)((long long)need[s] * (cap - B) / tot_need) + 1;
+        grid += ncta[s];
+    }
+    {
+        const size_t cap0 = ll_rows.cap;
+        ll_rows.reserve((size_t)grid * 32 + (size_t)B * kLlPoseLen);
+        if (ll_rows.cap != cap0) FLS_CUDA(cudaMemsetAsync(ll_rows.p, 0, ll_rows.cap * sizeof(uint4), stream));
+    }
+    match_epoch = (match_epoch + 1) & 0xffffffu;
+    if (match_epoch == 0) match_epoch = 1;
+    const size_t tbl_bytes = sizeof(NdtBatchItem) * (size_t)B;
+    if (tbl_bytes > h_batch_cap) {
+        if (h_batch) cudaFreeHost(h_batch);
+        h_batch = nullptr;
+        h_batch_cap = 0;
+        FLS_CUDA(cudaMallocHost(&h_batch, tbl_bytes * 2 + 65536));
+        h_batch_cap = tbl_bytes * 2 + 65536;
+    }
+    d_batch.reserve(tbl_bytes);
+    NdtBatchItem* items = reinterpret_cast<NdtBatchItem*>(h_batch);
+    uint4* pose_base = ll_rows.p + (size_t)grid * 32;
+    int cta0 = 0;
+    for (int s = 0; s < B; ++s) {
+        launch_gn_init(state.p + s, T + 16 * s, stream);
+        launches++;
+        NdtBatchItem& it = items[s];
+        std::memset(&it, 0, sizeof(it));
+        it.a.src = src_f.p + off[s];
+        it.a.n = (int)(off[s + 1] - off[s]);
+        it.a.map = ndt.view();
+        it.a.outlier_thres = cfg.ndt_outlier_thres;
+        it.a.state = state.p + s;
+        it.ctl.state = state.p + s;
+        it.ctl.ll_rows = ll_rows.p + (size_t)cta0 * 32;
+        it.ctl.ll_pose = pose_base + (size_t)s * kLlPoseLen;
+        it.ctl.tag_base = match_epoch << 8;
+        it.ctl.gp.method = FLS_NDT;
+        it.ctl.gp.max_iterations = cfg.max_iterations;
+        it.ctl.gp.min_effective = cfg.ndt_min_effective_pts;
+        it.ctl.gp.rot_thres = cfg.rotation_converge_thres;
+        it.ctl.gp.pos_thres = cfg.position_converge_thres;
+        it.ctl.log = log_cap ? log.p + (size_t)s * log_cap : nullptr;
+        it.ctl.log_cap = log_cap;
+        it.ctl.result = (result_buf && (size_t)s < result_cap) ? result_buf + (size_t)s * kResultLen : nullptr;
+        it.cta0 = cta0;
+        it.ncta = ncta[s];
+        cta0 += ncta[s];
+    }
+    FLS_CUDA(cudaMemcpyAsync(d_batch.p, h_batch, tbl_bytes, cudaMemcpyHostToDevice, stream));
+    h2d_bytes += (long long)tbl_bytes;
+    per_point_iter_bytes = 16 + 16LL * 7;
+    per_cand_bytes = 80;
+    per_hit_bytes = 0;
+    if (profile) FLS_CUDA(cudaEventRecord(prof_ev[0], stream));
+    launch_ndt_batch(reinterpret_cast<const NdtBatchItem*>(d_batch.p), B, grid, stream);
+    if (profile) FLS_CUDA(cudaEventRecord(prof_ev[1], stream));
+    launches++;
+    fused_loop = true;
+    last_src = src_f.p;
+    last_src_n = off[1];
+    FLS_CUDA(cudaMemcpyAsync(h_state, state.p, sizeof(GnState) * (size_t)B, cudaMemcpyDeviceToHost, stream));
+    d2h_bytes += (long long)(sizeof(GnState) * (size_t)B);
+    if (log_cap) {
+        FLS_CUDA(cudaMemcpyAsync(h_log.data(), log.p, sizeof(fls_iter_log) * log_cap, cudaMemcpyDeviceToHost, stream));
+        d2h_bytes += (long long)(sizeof(fls_iter_log) * log_cap);
+    }
+    end_call(st);
+    float kernel_ms = 0.f;
+    if (profile) FLS_CUDA(cudaEventElapsedTime(&kernel_ms, prof_ev[0], prof_ev[1]));
+    batch_n.clear();
+    for (int s = 0; s < B; ++s) {
+        const GnState& gs = h_state[s];
+        const long long ns = (long long)(off[s + 1] - off[s]);
+        batch_n.push_back(ns);
+        double* Ts = T + 16 * s;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) Ts[c * 4 + r] = gs.R[r * 3 + c];
+            Ts[12 + r] = gs.t[r];
+        }
+        Ts[3] = Ts[7] = Ts[11] = 0.0;
+        Ts[15] = 1.0;
+        if (converged) converged[s] = gs.converged;
+        if (st) {
+            fls_match_stats& o = st[s];
+            if (s > 0) std::memset(&o, 0, sizeof(o));
+            o.iterations = gs.iter;
+            o.converged = gs.converged;
+            o.n_source = ns;
+            o.n_valid = gs.n_valid;
+            o.sum_residual = gs.sum_res;
+            if (profile) {
+                o.algo_bytes = (long long)gs.iter * ns * per_point_iter_bytes + (long long)(gs.cand_total + 0.5) * per_cand_bytes;
+                o.kernel_ms = s == 0 ? kernel_ms : 0.f;
+                o.kernel_launches = s == 0 ? 1 : 0;
+            }
+        }
+    }
+    std::memcpy(T_final, T, sizeof(T_final));
+    log_n = h_state[0].iter < log_cap ? h_state[0].iter : log_cap;
     return FLS_OK;
 }
 
@@ -1014,7 +1151,7 @@ int fls_match_batch(fls_handle* hh, int n_scans, const void* const* planar, cons
                     fls_match_stats* st) {
     Handle* h = reinterpret_cast<Handle*>(hh);
     if (!h || !planar || !n || !T || n_scans < 1 || n_scans > fls::kMaxBatch || !stride_ok(stride)) return FLS_ERR_INVALID_ARG;
-    if (h->cfg.method != FLS_P2PLANE_IVOX) return FLS_ERR_UNSUPPORTED;
+    if (h->cfg.method != FLS_P2PLANE_IVOX && h->cfg.method != FLS_NDT) return FLS_ERR_UNSUPPORTED;
     // scans of one batch are matched against the same map state: only meaningful when Match does not modify the map
     if (n_scans > 1 && !h->cfg.localization_mode) return FLS_ERR_UNSUPPORTED;
     FLS_TRY
@@ -1043,6 +1180,7 @@ int fls_match_batch(fls_handle* hh, int n_scans, const void* const* planar, cons
         }
         off += n[s];
     }
+    if (h->cfg.method == FLS_NDT) return n_scans == 1 ? h->match_ndt(ptrs[0], n[0], T, converged, st) : h->match_ndt_batch(n_scans, ptrs, n, T, converged, st);
     if (n_scans == 1) return h->match_p2plane_ivox(ptrs[0], n[0], T, converged, st);
     return h->match_ivox_batch(n_scans, ptrs, n, T, converged, st);
     FLS_CATCH
@@ -1052,7 +1190,7 @@ int fls_match_batch_device(fls_handle* hh, int n_scans, const void* const* d_pla
                            fls_match_stats* st) {
     Handle* h = reinterpret_cast<Handle*>(hh);
     if (!h || !d_planar || !n || !T || n_scans < 1 || n_scans > fls::kMaxBatch) return FLS_ERR_INVALID_ARG;
-    if (h->cfg.method != FLS_P2PLANE_IVOX) return FLS_ERR_UNSUPPORTED;
+    if (h->cfg.method != FLS_P2PLANE_IVOX && h->cfg.method != FLS_NDT) return FLS_ERR_UNSUPPORTED;
     if (n_scans > 1 && !h->cfg.localization_mode) return FLS_ERR_UNSUPPORTED;
     FLS_TRY
     if (st) std::memset(st, 0, sizeof(*st) * (size_t)n_scans);
@@ -1062,6 +1200,7 @@ int fls_match_batch_device(fls_handle* hh, int n_scans, const void* const* d_pla
         if (!d_planar[s] && n[s]) return FLS_ERR_INVALID_ARG;
         ptrs[s] = static_cast<const float4*>(d_planar[s]);
     }
+    if (h->cfg.method == FLS_NDT) return n_scans == 1 ? h->match_ndt(ptrs[0], n[0], T, converged, st) : h->match_ndt_batch(n_scans, ptrs, n, T, converged, st);
     if (n_scans == 1) return h->match_p2plane_ivox(ptrs[0], n[0], T, converged, st);
     return h->match_ivox_batch(n_scans, ptrs, n, T, converged, st);
     FLS_CATCH
@@ -1091,6 +1230,38 @@ int fls_get_iter_log(const fls_handle* hh, fls_iter_log* out, int capacity) {
     return n;
 }
 
+int fls_get_voxel_keys(fls_handle* hh, int32_t* keys_xyz, size_t capacity, size_t* n) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || !n || (capacity && !keys_xyz)) return FLS_ERR_INVALID_ARG;
+    if (h->cfg.method != FLS_NDT && h->cfg.method != FLS_P2PLANE_IVOX) return FLS_ERR_UNSUPPORTED;
+    FLS_TRY
+    FLS_CUDA(cudaSetDevice(h->cfg.device));
+    std::vector<unsigned long long> packed(capacity + 1);
+    const size_t m = h->cfg.method == FLS_NDT ? h->ndt.dump_keys(packed.data(), capacity, h->stream) : h->ivox.dump_keys(packed.data(), capacity, h->stream);
+    for (size_t i = 0; i < m; ++i) {
+        const unsigned long long k = packed[i];
+        const int c[3] = {(int)((k >> 42) & 0x1fffffu), (int)((k >> 21) & 0x1fffffu), (int)(k & 0x1fffffu)};
+        for (int a = 0; a < 3; ++a) keys_xyz[3 * i + a] = (c[a] & 0x100000) ? c[a] - 0x200000 : c[a];  // 21-bit two's complement
+    }
+    *n = h->cfg.method == FLS_NDT ? h->ndt.n_vox : h->ivox.n_vox;
+    return FLS_OK;
+    FLS_CATCH
+}
+
+int fls_get_map_points(fls_handle* hh, float* xyzi, size_t capacity, size_t* n) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || !n || (capacity && !xyzi)) return FLS_ERR_INVALID_ARG;
+    if (h->cfg.method != FLS_P2PLANE_IVOX) return FLS_ERR_UNSUPPORTED;
+    FLS_TRY
+    FLS_CUDA(cudaSetDevice(h->cfg.device));
+    FLS_CUDA(cudaStreamSynchronize(h->stream));
+    const size_t m = h->ivox.n_pts < capacity ? h->ivox.n_pts : capacity;
+    if (m) FLS_CUDA(cudaMemcpy(xyzi, h->ivox.pts_all.p, m * sizeof(float4), cudaMemcpyDeviceToHost));
+    *n = h->ivox.n_pts;
+    return FLS_OK;
+    FLS_CATCH
+}
+
 int fls_get_map_info(const fls_handle* hh, fls_map_info* out) {
     const Handle* h = reinterpret_cast<const Handle*>(hh);
     if (!h || !out) return FLS_ERR_INVALID_ARG;
@@ -1117,6 +1288,21 @@ int fls_get_map_info(const fls_handle* hh, fls_map_info* out) {
         out->bytes = (long long)(h->kd_planar.grid.bytes() + h->kd_planar.cloud.bytes() + (full ? h->kd_corner.grid.bytes() + h->kd_corner.cloud.bytes() : 0));
     }
     return FLS_OK;
+}
+
+int fls_ivox_add_points(fls_handle* hh, const void* pts, size_t n, size_t stride) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || (!pts && n) || !stride_ok(stride)) return FLS_ERR_INVALID_ARG;
+    if (h->cfg.method != FLS_P2PLANE_IVOX) return FLS_ERR_UNSUPPORTED;
+    FLS_TRY
+    h->begin_call();
+    const float4* d = h->upload(pts, n, stride, h->stage);
+    const int rc = h->ivox.append_and_build(d, n, h->cfg.ivox_capacity, h->stream);
+    h->launches += h->ivox.launches;
+    h->ivox.launches = 0;
+    h->end_call(nullptr);
+    return rc;
+    FLS_CATCH
 }
 
 int fls_ivox_knn(fls_handle* hh, const void* queries, size_t n, size_t stride, int k, float* out_pts, int32_t* out_count) {

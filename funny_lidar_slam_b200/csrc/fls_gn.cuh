@@ -205,7 +205,12 @@ __device__ inline void gn_step_pre(GnState* s, const GnPre& q, const double* tot
 // record.  Needs co-resident CTAs (cooperative launch).  On return s_pose[0..11] (shared memory, row-major R then t) holds
 // the pose of the next iteration; returns true when the loop is finished.
 template <int BLOCK>
-__device__ __forceinline__ bool gn_handover(double (&acc)[kNumAcc], const GnLoopCtl& c, int it, double* s_pose) {
+__device__ __forceinline__ bool gn_handover(double (&acc)[kNumAcc], const GnLoopCtl& c, int it, double* s_pose, int cta = -1, int ncta = -1) {
+    // (cta, ncta): position of this CTA in the sub-grid that serves the scan (batch launches); default: the whole grid
+    if (cta < 0) {
+        cta = (int)blockIdx.x;
+        ncta = (int)gridDim.x;
+    }
     constexpr int W = BLOCK / 32;
     __shared__ double s_red[W][kAccStride];
     __shared__ int s_stop;
@@ -224,13 +229,13 @@ __device__ __forceinline__ bool gn_handover(double (&acc)[kNumAcc], const GnLoop
         double v = 0;
 #pragma unroll
         for (int w = 0; w < W; ++w) v += s_red[w][lane];
-        ll_store(c.ll_rows + (size_t)blockIdx.x * 32 + lane, v, tag);
+        ll_store(c.ll_rows + (size_t)cta * 32 + lane, v, tag);
     }
-    if (blockIdx.x == 0) {
+    if (cta == 0) {
         GnPre pre;
         if (threadIdx.x == 0) gn_load(c.state, pre);
         __syncthreads();  // s_red is free again
-        const int nrows = (int)gridDim.x;
+        const int nrows = ncta;
         double sum;
         for (;;) {
             bool ok = true;

@@ -112,6 +112,7 @@ struct Handle {
 
     int add_cloud_ndt(const float4* d_cloud, size_t n);
     int match_ndt(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st);
+    int match_ndt_batch(int n_scans, const float4* const* d_scans, const size_t* n, double* T, int* converged, fls_match_stats* st);
 
     int add_cloud_icp(const float4* d_cloud, size_t n);
     int match_icp(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st);

@@ -72,6 +72,15 @@ struct NdtArgs {
 };
 int ndt_grid(int n, int device);  // co-resident grid of the persistent kernel
 void launch_ndt_loop(const NdtArgs& a, const GnLoopCtl& ctl, int grid, cudaStream_t st);
+// batch of scans in one launch: scan s is served by CTAs [cta0, cta0 + ncta) of the grid (its own persistent loop)
+struct __align__(16) NdtBatchItem {
+    NdtArgs a;
+    GnLoopCtl ctl;
+    int cta0, ncta;
+    int pad[2];
+};
+int ndt_max_grid(int device);  // co-resident CTAs of the batch kernel
+void launch_ndt_batch(const NdtBatchItem* d_items, int n_scans, int grid, cudaStream_t st);
 
 struct IcpArgs {
     const float4* __restrict__ src;  // voxel-filtered scan, body frame

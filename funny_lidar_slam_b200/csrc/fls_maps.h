@@ -1,8 +1,21 @@
 // fls_maps.h — host-side owners of the device-resident map structures.
 #pragma once
+#include <vector>
+
 #include "fls_common.cuh"
 
 namespace fls {
+
+// Exact emulation of upstream's LRU policy for one insert call (IVoxMap::AddPoints, ivox_map.cpp:122-143; IncrementalNDT::
+// AddCloudToLocalMap, incremental_ndt.h:193-214): points are inserted one after the other, a touched voxel moves to the front,
+// a created voxel is pushed to the front and — when the size then reaches `capacity` — the tail is popped.
+//   cand_first_touch[i]: candidates = voxels that existed before the call, oldest first; value = index of the first point of
+//                        this call that touches it (0xffffffff: untouched)
+//   create_times       : index of the point that creates each new voxel (any order)
+// Output: victims (positions in the candidate list) in eviction order, and for each whether the voxel is touched again later in
+// the call (it is then re-created empty).  Returns false when the candidates run out (the call alone overflows the capacity).
+bool lru_simulate(size_t size0, size_t capacity, const std::vector<unsigned>& cand_first_touch, std::vector<unsigned> create_times,
+                  std::vector<unsigned>& victims, std::vector<unsigned char>& recreated);
 
 // scratch shared by the sort / run-length passes of every map build and of the voxel-grid filter
 struct BuildScratch {
@@ -35,6 +48,12 @@ struct IvoxMap {
     size_t n_pts = 0, n_vox = 0;
     unsigned mask = 0;
     DevBuf<float4> pts_all;     // insertion order (kept so incremental adds can rebuild)
+    DevBuf<unsigned long long> stamp_all;  // per point of pts_all: (AddPoints call << 32) | position in that call — LRU state (capacity > 0 only)
+    unsigned long long call_no = 0;
+    DevBuf<unsigned> lru_old, lru_first, lru_nold, lru_vals, lru_vals_sorted;
+    DevBuf<unsigned long long> lru_keys, lru_keys_sorted;
+    DevBuf<unsigned char> lru_flags;
+    DevBuf<int> lru_cnt;
     DevBuf<float4> pts_sorted;  // voxel-contiguous, Morton order
     DevBuf<HashSlot> table;     // occupied voxels
     // stencil lists
@@ -52,6 +71,9 @@ struct IvoxMap {
         inv_res = 1.0f / r;
     }
     void clear() { n_pts = n_vox = n_centers = n_list = 0; }
+    int sort_and_runs(size_t n, cudaStream_t st, int* runs_out);
+    int evict_lru(size_t n_old, size_t n, int runs, long long capacity, cudaStream_t st, size_t* n_after);
+    size_t dump_keys(unsigned long long* h_out, size_t cap, cudaStream_t st);  // packed keys of the occupied voxels (tests)
     // append n points that are already on the device (packed float4) and rebuild; returns fls_status
     int append_and_build(const float4* d_new, size_t n_new, long long capacity, cudaStream_t st);
     int build_stencil_lists(cudaStream_t st);
@@ -71,7 +93,10 @@ struct NdtCold {
     int num_points;   // VoxelData::num_points_
     int carry_count;  // points buffered and not yet consumed by an estimate (<= min_points_in_voxel)
     int estimated;
-    int pad;
+    int alive;                  // 0 once the voxel has been evicted (its index is on the free list)
+    unsigned long long key;     // packed voxel key (table rebuild after evictions)
+    unsigned long long stamp;   // last touch: (AddCloudToLocalMap call << 32) | index of the touching point in that call's cloud —
+                                // the position of the voxel in upstream's LRU list (incremental_ndt.h:193-214)
 };
 // table slot: {packed key, voxel index, estimated flag}
 struct NdtView {
@@ -93,11 +118,24 @@ struct NdtMap {
     DevBuf<NdtCold> cold;
     DevBuf<double> carry;  // [capacity][min_pts][3]
     DevBuf<float4> filtered;
-    DevBuf<int> counter;  // device voxel counter
+    DevBuf<int> counter;  // device voxel counter (high-water mark of allocated indices), overflow flag, free-list cursor, creations
+    DevBuf<int> free_list;         // indices of evicted voxels, reused by the next creations
+    int n_free = 0;
+    int hi_water = 0;              // voxel indices handed out so far
+    unsigned long long call_no = 0;  // AddCloudToLocalMap calls so far (high half of the LRU stamps)
+    DevBuf<int> run_vi;            // per touched voxel of a call: its index, -1 = to be created
+    DevBuf<int> touch_run;         // per voxel index: the run that touches it in this call, -1 = none
+    DevBuf<unsigned long long> lru_keys, lru_keys_sorted;
+    DevBuf<unsigned> lru_vals, lru_vals_sorted;
+    std::vector<int> h_buf;
     BuildScratch scratch;
     int launches = 0;
 
     void configure(double voxel_size, int min_points, int max_points, long long cap);
+    // evict the LRU tail exactly as upstream's sequential insert would (incremental_ndt.h:203-206); called by add_cloud
+    int evict_lru(int runs, int n_new, int n_touched, cudaStream_t st, int* n_victims, int* n_recreated);
+    // packed voxel keys of the live voxels (tests); returns how many
+    size_t dump_keys(unsigned long long* h_out, size_t cap, cudaStream_t st);
     // VoxelGridCloud(cloud, leaf) then insert/update voxels; `first_scan` = flag_first_scan_ upstream
     int add_cloud(const float4* d_cloud, size_t n, float leaf, bool first_scan, cudaStream_t st);
     NdtView view() const {

@@ -6,7 +6,8 @@
 //   * hot    : 80-byte records {mu, symmetric information} — the only thing the Match kernel reads
 //   * cold   : sigma, counters and a carry buffer of <= min_points_in_voxel pending points per voxel, touched only
 //              by AddCloudToLocalMap / UpdateVoxel (:130-227)
-// LRU eviction at `capacity` is not emulated (FLS_ERR_CAPACITY when the voxel count would reach it).
+// LRU eviction at `capacity` (:203-206) is emulated exactly: stamps per voxel + a host simulation of the sequential insert
+// (NdtMap::evict_lru, lru_simulate in fls_map.cu).
 #include <cub/cub.cuh>
 
 #include "fls_gn.cuh"
@@ -62,7 +63,10 @@ struct NdtUpdateArgs {
     NdtHot* hot;
     NdtCold* cold;
     double* carry;
-    int* counter;
+    int* counter;  // [0] high-water mark of voxel indices, [1] overflow flag, [2] free-list cursor
+    const int* free_list;
+    int n_free;
+    unsigned long long call_hi;  // call number << 32
     long long capacity;
     int min_pts, max_pts;
     int first_scan;
@@ -121,10 +125,12 @@ __global__ void ndt_update_kernel(NdtUpdateArgs a, int* overflow) {
     for (;;) {
         const unsigned long long prev = atomicCAS(&a.tab[h].key, kEmptyKey, key);
         if (prev == kEmptyKey) {
-            const int id = atomicAdd(a.counter, 1);
-            if ((long long)id + 1 >= a.capacity) {  // data_.size() >= capacity_ would evict the LRU tail upstream (:203-206)
-                atomicExch(overflow, 1);
-            }
+            // indices of evicted voxels first (the LRU tail was evicted before this kernel: NdtMap::evict_lru), then fresh ones
+            int id;
+            const int k = atomicAdd(a.counter + 2, 1);
+            if (k < a.n_free) id = a.free_list[a.n_free - 1 - k];  // the list is a stack
+            else id = atomicAdd(a.counter, 1);
+            if ((long long)id >= a.capacity) atomicExch(overflow, 1);  // cannot happen once the eviction ran
             vi = (unsigned)id;
             a.tab[h].start = vi;
             created = true;
@@ -143,8 +149,11 @@ __global__ void ndt_update_kernel(NdtUpdateArgs a, int* overflow) {
         cd.num_points = 0;
         cd.carry_count = 0;
         cd.estimated = 0;
+        cd.alive = 1;
+        cd.key = key;
         for (int k = 0; k < 9; ++k) cd.sigma[k] = 0;
     }
+    cd.stamp = a.call_hi | (unsigned long long)a.idx_sorted[s + c - 1];  // moved to the front by its last point of this call (:208-210)
     if (!cd.estimated) cd.num_points += (int)c;  // VoxelData ctor / AddPoint (:66-76): counted only before the first estimate
 
     double mu[3], info[9];
@@ -210,11 +219,88 @@ __global__ void ndt_update_kernel(NdtUpdateArgs a, int* overflow) {
     }
 }
 
+// ---- LRU bookkeeping (incremental_ndt.h:193-214) -------------------------------------------------------------------------------
+// which touched voxels exist already; counters[3] = to be created, counters[4] = existing and touched
+__global__ void ndt_lookup_kernel(int runs, const unsigned long long* __restrict__ run_keys, const HashSlot* __restrict__ tab, unsigned mask,
+                                  int* __restrict__ run_vi, int* __restrict__ touch_run, int* counters) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= runs) return;
+    unsigned vi, est;
+    if (table_find(tab, mask, run_keys[r], vi, est)) {
+        run_vi[r] = (int)vi;
+        touch_run[vi] = r;
+        atomicAdd(counters + 4, 1);
+    } else {
+        run_vi[r] = -1;
+        atomicAdd(counters + 3, 1);
+    }
+}
+__global__ void ndt_live_kernel(const NdtCold* __restrict__ cold, int hi_water, unsigned long long* __restrict__ stamps, unsigned* __restrict__ vis,
+                                int* counters) {
+    const int vi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vi >= hi_water || !cold[vi].alive) return;
+    const int pos = atomicAdd(counters + 5, 1);
+    stamps[pos] = cold[vi].stamp;
+    vis[pos] = (unsigned)vi;
+}
+// first point of this call that touches candidate k (0xffffffff: none)
+__global__ void ndt_cand_kernel(const unsigned* __restrict__ vis_sorted, int K, const int* __restrict__ touch_run, const unsigned* __restrict__ starts,
+                                const unsigned* __restrict__ idx_sorted, unsigned* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int r = touch_run[vis_sorted[k]];
+    out[k] = r >= 0 ? idx_sorted[starts[r]] : 0xffffffffu;
+}
+__global__ void ndt_create_times_kernel(int runs, const int* __restrict__ run_vi, const unsigned* __restrict__ starts,
+                                        const unsigned* __restrict__ idx_sorted, unsigned* __restrict__ out, int* cursor) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= runs || run_vi[r] >= 0) return;
+    out[atomicAdd(cursor, 1)] = idx_sorted[starts[r]];
+}
+__global__ void ndt_evict_kernel(const unsigned* __restrict__ victim_pos, const unsigned char* __restrict__ recreated, int n,
+                                 const unsigned* __restrict__ vis_sorted, NdtCold* __restrict__ cold, int* __restrict__ free_list, int free_base,
+                                 const int* __restrict__ touch_run, int* __restrict__ run_vi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned vi = vis_sorted[victim_pos[i]];
+    cold[vi].alive = 0;
+    free_list[free_base + i] = (int)vi;
+    if (recreated[i]) run_vi[touch_run[vi]] = -1;  // touched again later in the call: created anew, empty (:197-201)
+}
+__global__ void ndt_table_rebuild_kernel(const NdtCold* __restrict__ cold, int hi_water, HashSlot* tab, unsigned mask) {
+    const int vi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vi >= hi_water || !cold[vi].alive) return;
+    const unsigned long long key = cold[vi].key;
+    unsigned h = hash_key(key) & mask;
+    for (;;) {
+        const unsigned long long prev = atomicCAS(&tab[h].key, kEmptyKey, key);
+        if (prev == kEmptyKey) {
+            tab[h].start = (unsigned)vi;
+            tab[h].count = cold[vi].estimated ? 1u : 0u;
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+}
+__global__ void ndt_table_clear_only_kernel(HashSlot* tab, size_t slots) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < slots) {
+        tab[i].key = kEmptyKey;
+        tab[i].start = 0xffffffffu;
+        tab[i].count = 0;
+    }
+}
+__global__ void ndt_dump_keys_kernel(const NdtCold* __restrict__ cold, int hi_water, unsigned long long* __restrict__ out, int* cursor) {
+    const int vi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vi >= hi_water || !cold[vi].alive) return;
+    out[atomicAdd(cursor, 1)] = cold[vi].key;
+}
+
 // ---- K2: NDT residual kernel -----------------------------------------------------------------------------------
 // One persistent launch runs every Gauss-Newton iteration of a Match (gn_handover, fls_gn.cuh): grid-stride over the
 // points, per-thread sums, CTA row, last-CTA fold + solve + release.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) ndt_gn_kernel(NdtArgs a, GnLoopCtl ctl) {
+__device__ __forceinline__ void ndt_gn_loop(const NdtArgs& a, const GnLoopCtl& ctl, const int cta, const int ncta) {
     __shared__ double s_pose[12];
     if (threadIdx.x < 9) s_pose[threadIdx.x] = __ldcg(&a.state->R[threadIdx.x]);
     else if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(&a.state->t[threadIdx.x - 9]);
@@ -224,7 +310,7 @@ __global__ void __launch_bounds__(BLOCK) ndt_gn_kernel(NdtArgs a, GnLoopCtl ctl)
 #pragma unroll
     for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.0;
 
-    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < a.n; i += gridDim.x * BLOCK) {
+    for (int i = cta * BLOCK + threadIdx.x; i < a.n; i += ncta * BLOCK) {
         const float4 sp = a.src[i];
         const double px = sp.x, py = sp.y, pz = sp.z;
         const double* R = s_pose;
@@ -293,8 +379,35 @@ __global__ void __launch_bounds__(BLOCK) ndt_gn_kernel(NdtArgs a, GnLoopCtl ctl)
             acc[kAccRes] += chis;
         }
     }
-    if (gn_handover<BLOCK>(acc, ctl, it, s_pose)) break;
+    if (gn_handover<BLOCK>(acc, ctl, it, s_pose, cta, ncta)) break;
     }
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) ndt_gn_kernel(NdtArgs a, GnLoopCtl ctl) {
+    ndt_gn_loop<BLOCK>(a, ctl, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// A batch of independent scans against the same (static) map in ONE cooperative launch: the grid is cut into one sub-grid
+// per scan, each running its own persistent Gauss-Newton loop (own rows, pose record and state) — the ~15 us hand-over of a
+// scan overlaps with the residual passes of the others, which is what the single-scan loop cannot hide at these sizes.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) ndt_gn_batch_kernel(const NdtBatchItem* __restrict__ items, int n_scans) {
+    __shared__ NdtBatchItem s_item;
+    __shared__ int s_which;
+    if (threadIdx.x == 0) {
+        int w = 0;
+        while (w + 1 < n_scans && (int)blockIdx.x >= items[w + 1].cta0) ++w;
+        s_which = w;
+    }
+    __syncthreads();
+    {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(items + s_which);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_item);
+        for (int k = threadIdx.x; k < (int)(sizeof(NdtBatchItem) / 8); k += BLOCK) dst[k] = src[k];
+    }
+    __syncthreads();
+    ndt_gn_loop<BLOCK>(s_item.a, s_item.ctl, (int)blockIdx.x - s_item.cta0, s_item.ncta);
 }
 
 }  // namespace
@@ -317,6 +430,22 @@ void launch_ndt_loop(const NdtArgs& a, const GnLoopCtl& ctl, int grid, cudaStrea
     GnLoopCtl c_ = ctl;
     void* params[] = {&a_, &c_};
     FLS_CUDA(cudaLaunchCooperativeKernel((const void*)ndt_gn_kernel<kNdtBlock>, dim3(grid), dim3(kNdtBlock), params, 0, st));
+}
+
+int ndt_max_grid(int device) {
+    ndt_grid(1, device);  // fills the cache
+    static int cap[64] = {0};
+    if (device >= 0 && device < 64 && !cap[device]) {
+        int sms = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ndt_gn_batch_kernel<kNdtBlock>, kNdtBlock, 0);
+        cap[device] = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    return (device >= 0 && device < 64) ? cap[device] : 148;
+}
+void launch_ndt_batch(const NdtBatchItem* d_items, int n_scans, int grid, cudaStream_t st) {
+    void* params[] = {&d_items, &n_scans};
+    FLS_CUDA(cudaLaunchCooperativeKernel((const void*)ndt_gn_batch_kernel<kNdtBlock>, dim3(grid), dim3(kNdtBlock), params, 0, st));
 }
 
 void NdtMap::configure(double voxel_size, int min_points, int max_points, long long cap) {
@@ -343,7 +472,7 @@ int NdtMap::add_cloud(const float4* d_cloud, size_t n, float leaf, bool first_sc
         hot.reserve((size_t)capacity);
         cold.reserve((size_t)capacity);
         carry.reserve((size_t)capacity * (size_t)(min_pts > 0 ? min_pts : 1) * 3);
-        counter.reserve(2);
+        counter.reserve(8);
         ndt_table_clear_kernel<<<grid_for(slots, 256), 256, 0, st>>>(table.p, slots, counter.p);
         launches++;
     }
@@ -373,6 +502,26 @@ int NdtMap::add_cloud(const float4* d_cloud, size_t n, float leaf, bool first_sc
     const int runs = *sc.h_num_runs;
     tb = sc.cub_tmp.cap;
     FLS_CUDA(cub::DeviceScan::ExclusiveSum(sc.cub_tmp.p, tb, sc.counts.p, sc.starts.p, runs, st));
+    // ---- LRU bookkeeping: which touched voxels exist, how many are created, who has to go first --------------------------------
+    const int hi_water0 = hi_water;
+    run_vi.reserve((size_t)runs + 1);
+    touch_run.reserve((size_t)capacity + 1);
+    free_list.reserve((size_t)capacity + 1);
+    FLS_CUDA(cudaMemsetAsync(counter.p + 1, 0, 7 * sizeof(int), st));
+    if (hi_water0 > 0) FLS_CUDA(cudaMemsetAsync(touch_run.p, 0xff, sizeof(int) * (size_t)hi_water0, st));
+    ndt_lookup_kernel<<<grid_for(runs, 256), 256, 0, st>>>(runs, sc.uniq.p, table.p, mask, run_vi.p, touch_run.p, counter.p);
+    int hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    FLS_CUDA(cudaMemcpyAsync(hc, counter.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FLS_CUDA(cudaStreamSynchronize(st));
+    launches += 1;
+    const int n_new = hc[3], n_touched = hc[4];
+    ++call_no;
+    int n_victims = 0, n_recreated = 0;
+    // upstream: after every creation `if (data_.size() >= capacity_) pop_back()` (:203-206) — the list never holds `capacity` voxels
+    if ((long long)n_vox + n_new >= capacity) {
+        const int rc = evict_lru(runs, n_new, n_touched, st, &n_victims, &n_recreated);
+        if (rc != FLS_OK) return rc;
+    }
     NdtUpdateArgs ua;
     ua.pts = filtered.p;
     ua.idx_sorted = sc.idx_sorted.p;
@@ -386,20 +535,91 @@ int NdtMap::add_cloud(const float4* d_cloud, size_t n, float leaf, bool first_sc
     ua.cold = cold.p;
     ua.carry = carry.p;
     ua.counter = counter.p;
+    ua.free_list = free_list.p;
+    ua.n_free = n_free;
+    ua.call_hi = call_no << 32;
     ua.capacity = capacity;
     ua.min_pts = min_pts;
     ua.max_pts = max_pts;
     ua.first_scan = first_scan ? 1 : 0;
     int* overflow = counter.p + 1;
-    FLS_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
+    FLS_CUDA(cudaMemsetAsync(counter.p + 1, 0, 2 * sizeof(int), st));  // overflow flag, free-list cursor
     ndt_update_kernel<<<grid_for(runs, 128), 128, 0, st>>>(ua, overflow);
-    int h[2] = {0, 0};
-    FLS_CUDA(cudaMemcpyAsync(h, counter.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    int h[3] = {0, 0, 0};
+    FLS_CUDA(cudaMemcpyAsync(h, counter.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     FLS_CUDA(cudaStreamSynchronize(st));
     launches += 6;
-    n_vox = (size_t)h[0];
+    hi_water = h[0];
+    n_free -= h[2] < n_free ? h[2] : n_free;  // the creations popped that many indices off the free stack
+    n_vox = n_vox + (size_t)n_new + (size_t)n_recreated - (size_t)n_victims;
     if (h[1]) return FLS_ERR_CAPACITY;
     return FLS_OK;
+}
+
+// Evicts what upstream's sequential insert would evict during this call (exact, including a victim that is touched again later in
+// the call): candidates = live voxels by ascending stamp, simulated on the host against the creation times of the new voxels.
+int NdtMap::evict_lru(int runs, int n_new, int n_touched, cudaStream_t st, int* n_victims, int* n_recreated) {
+    BuildScratch& sc = scratch;
+    const int hw = hi_water;
+    const size_t n_live = n_vox;
+    if (n_live == 0) return FLS_ERR_CAPACITY;  // the first cloud alone overflows the capacity: upstream dereferences an erased voxel (:216-220)
+    lru_keys.reserve(n_live + 1);
+    lru_keys_sorted.reserve(n_live + 1);
+    lru_vals.reserve(n_live + 1);
+    lru_vals_sorted.reserve(n_live + 1);
+    ndt_live_kernel<<<grid_for(hw, 256), 256, 0, st>>>(cold.p, hw, lru_keys.p, lru_vals.p, counter.p);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, lru_keys.p, lru_keys_sorted.p, lru_vals.p, lru_vals_sorted.p, (int)n_live, 0, 64, st);
+    sc.cub_tmp.reserve(tb + 256);
+    tb = sc.cub_tmp.cap;
+    FLS_CUDA(cub::DeviceRadixSort::SortPairs(sc.cub_tmp.p, tb, lru_keys.p, lru_keys_sorted.p, lru_vals.p, lru_vals_sorted.p, (int)n_live, 0, 64, st));
+    // the eviction count without cascades is n_vox + n_new - (capacity - 1); every skipped candidate was touched in this call
+    const long long e0 = (long long)n_live + n_new - (capacity - 1);
+    size_t K = (size_t)(e0 > 0 ? e0 : 0) + 2 * (size_t)n_touched + 64;
+    if (K > n_live) K = n_live;
+    sc.k32a.reserve(K + 1);
+    sc.k32b.reserve((size_t)n_new + 1);
+    ndt_cand_kernel<<<grid_for(K, 256), 256, 0, st>>>(lru_vals_sorted.p, (int)K, touch_run.p, sc.starts.p, sc.idx_sorted.p, sc.k32a.p);
+    FLS_CUDA(cudaMemsetAsync(counter.p + 6, 0, sizeof(int), st));
+    ndt_create_times_kernel<<<grid_for(runs, 256), 256, 0, st>>>(runs, run_vi.p, sc.starts.p, sc.idx_sorted.p, sc.k32b.p, counter.p + 6);
+    std::vector<unsigned> cand(K), creat((size_t)n_new);
+    FLS_CUDA(cudaMemcpyAsync(cand.data(), sc.k32a.p, sizeof(unsigned) * K, cudaMemcpyDeviceToHost, st));
+    if (n_new) FLS_CUDA(cudaMemcpyAsync(creat.data(), sc.k32b.p, sizeof(unsigned) * (size_t)n_new, cudaMemcpyDeviceToHost, st));
+    FLS_CUDA(cudaStreamSynchronize(st));
+    launches += 5;
+    std::vector<unsigned> victims;
+    std::vector<unsigned char> recreated;
+    if (!lru_simulate(n_live, (size_t)capacity, cand, creat, victims, recreated)) return FLS_ERR_CAPACITY;
+    *n_victims = (int)victims.size();
+    *n_recreated = 0;
+    for (unsigned char r : recreated) *n_recreated += r ? 1 : 0;
+    if (victims.empty()) return FLS_OK;
+    // victims -> free list, their keys out of the table (rebuild: open addressing has no cheap delete)
+    sc.k32a.reserve(victims.size() + 1);
+    sc.minmax.reserve(victims.size() / 4 + 16);
+    FLS_CUDA(cudaMemcpyAsync(sc.k32a.p, victims.data(), sizeof(unsigned) * victims.size(), cudaMemcpyHostToDevice, st));
+    FLS_CUDA(cudaMemcpyAsync(sc.minmax.p, recreated.data(), victims.size(), cudaMemcpyHostToDevice, st));
+    ndt_evict_kernel<<<grid_for(victims.size(), 128), 128, 0, st>>>(sc.k32a.p, reinterpret_cast<const unsigned char*>(sc.minmax.p), (int)victims.size(),
+                                                                   lru_vals_sorted.p, cold.p, free_list.p, n_free, touch_run.p, run_vi.p);
+    n_free += (int)victims.size();
+    ndt_table_clear_only_kernel<<<grid_for(slots, 256), 256, 0, st>>>(table.p, slots);
+    ndt_table_rebuild_kernel<<<grid_for(hw, 256), 256, 0, st>>>(cold.p, hw, table.p, mask);
+    FLS_CUDA(cudaStreamSynchronize(st));  // the host vectors above are read by the copies
+    launches += 3;
+    return FLS_OK;
+}
+
+size_t NdtMap::dump_keys(unsigned long long* h_out, size_t cap, cudaStream_t st) {
+    if (n_vox == 0 || hi_water == 0) return 0;
+    lru_keys.reserve(n_vox + 1);
+    FLS_CUDA(cudaMemsetAsync(counter.p + 7, 0, sizeof(int), st));
+    ndt_dump_keys_kernel<<<grid_for(hi_water, 256), 256, 0, st>>>(cold.p, hi_water, lru_keys.p, counter.p + 7);
+    int n = 0;
+    FLS_CUDA(cudaMemcpyAsync(&n, counter.p + 7, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FLS_CUDA(cudaStreamSynchronize(st));
+    const size_t m = (size_t)n < cap ? (size_t)n : cap;
+    FLS_CUDA(cudaMemcpy(h_out, lru_keys.p, sizeof(unsigned long long) * m, cudaMemcpyDeviceToHost));
+    return m;
 }
 
 }  // namespace fls

@@ -144,6 +144,22 @@ class Registration:
         return bool(conv.value)
 
     # -- introspection ---------------------------------------------------------------------------------
+    def map_points(self) -> np.ndarray:
+        """(n, 4) float32 points of the LOAM-iVox map, insertion order."""
+        cap = max(int(self.map_info().n_points), 1)
+        out = np.zeros((cap, 4), np.float32)
+        n = C.c_size_t(0)
+        check(lib().fls_get_map_points(self._h, out.ctypes.data_as(C.c_void_p), cap, C.byref(n)), "fls_get_map_points")
+        return out[:min(cap, n.value)]
+
+    def voxel_keys(self) -> np.ndarray:
+        """(n, 3) int32 voxel keys the map currently holds (NDT / LOAM-iVox), unordered."""
+        cap = max(int(self.map_info().n_voxels), 1)
+        out = np.zeros((cap, 3), np.int32)
+        n = C.c_size_t(0)
+        check(lib().fls_get_voxel_keys(self._h, out.ctypes.data_as(C.c_void_p), cap, C.byref(n)), "fls_get_voxel_keys")
+        return out[:min(cap, n.value)]
+
     def iter_log(self):
         cap = max(1, self.cfg.max_iterations)
         buf = (FlsIterLog * cap)()
@@ -157,6 +173,11 @@ class Registration:
         mi = FlsMapInfo()
         check(lib().fls_get_map_info(self._h, C.byref(mi)), "fls_get_map_info")
         return mi
+
+    def ivox_add_points(self, pts: np.ndarray) -> None:
+        """IVoxMap::AddPoints: append map-frame points (LRU at ivox_capacity), no insertion rule."""
+        p, n, s, keep = _cloud(pts)
+        check(lib().fls_ivox_add_points(self._h, p, n, s), "fls_ivox_add_points")
 
     def ivox_knn(self, queries: np.ndarray, k: int = 5):
         p, n, s, keep = _cloud(queries)

@@ -173,7 +173,9 @@ int fls_fitness(fls_handle* h, float max_range, float* score);
 
 /* Batched Match for throughput (the benchmark entry SURVEY.md §8b names): `n_scans` (<= 64) independent scans, each with its
  * own in-out pose T[s*16 .. s*16+15], converged[s] and stats[s], matched against the same map in ONE persistent launch.
- * Implemented for FLS_P2PLANE_IVOX; more than one scan requires localization_mode (Match must not modify the map).
+ * Implemented for FLS_P2PLANE_IVOX (one persistent work-queue kernel for the batch) and FLS_NDT (one cooperative launch, a
+ * sub-grid and a Gauss-Newton loop per scan); more than one scan requires localization_mode (Match must not modify the map).
+ * For the LOAM-iVox plug-in the entry reads the planar clouds, for NDT the ordered clouds of the scans.
  * Call-level figures (gpu_ms, gpu_launches, byte counts, kernel_ms) are reported in stats[0]; per-scan fields everywhere.
  * Results are identical to n_scans separate fls_match calls.  The _device variant takes device pointers to packed float4 scans. */
 int fls_match_batch(fls_handle* h, int n_scans, const void* const* planar, const size_t* n, size_t stride_bytes, double* T_colmajor,
@@ -192,9 +194,20 @@ int fls_set_result_buffer_device(fls_handle* h, double* d_results, size_t capaci
 int fls_get_iter_log(const fls_handle* h, fls_iter_log* out, int capacity);
 
 int fls_get_map_info(const fls_handle* h, fls_map_info* out);
+/* Keys (x, y, z voxel coordinates, int32 triples) of the voxels the map currently holds, in no particular order: FLS_NDT
+ * (IncrementalNDT::grids_, incremental_ndt.h:393) and FLS_P2PLANE_IVOX (IVoxMap::grids_map_, ivox_map.h:70).  Introspection for the
+ * LRU parity tests; writes at most `capacity` triples and returns the voxel count in *n. */
+int fls_get_voxel_keys(fls_handle* h, int32_t* keys_xyz, size_t capacity, size_t* n);
+/* The points the FLS_P2PLANE_IVOX map holds (packed x, y, z, intensity), in insertion order; at most `capacity` points are written, the
+ * count is returned in *n.  Introspection for the map parity tests. */
+int fls_get_map_points(fls_handle* h, float* xyzi, size_t capacity, size_t* n);
 
 /* Test hook: IVoxMap::GetClosestPoint for a batch of map-frame queries (packed float4 host arrays).
  * out_pts receives n*k packed points (unused slots zero), out_count the number found per query. */
+/* IVoxMap::AddPoints (include/ivox_map/ivox_map.h:44, src/ivox_map/ivox_map.cpp:122-143): the points enter the FLS_P2PLANE_IVOX map as
+ * they are (map frame, no insertion rule), in order, with upstream's LRU policy at `ivox_capacity`.  The map of a handle in
+ * localization mode is otherwise replaced by fls_add_cloud; this entry appends. */
+int fls_ivox_add_points(fls_handle* h, const void* pts, size_t n, size_t stride_bytes);
 int fls_ivox_knn(fls_handle* h, const void* queries, size_t n, size_t stride_bytes, int k, float* out_pts, int32_t* out_count);
 
 /* VoxelGridCloud on the device: `out` must hold n packed float4 records; *n_out receives the count. */

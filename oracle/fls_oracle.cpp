@@ -284,6 +284,11 @@ size_t orc_reg_map_points(void* h) {
 size_t orc_reg_map_copy(void* h, int which, float* out, size_t cap) {
     auto* r = static_cast<Reg*>(h);
     const Cloud* m = nullptr;
+    Cloud iv;
+    if (r->p2p) {  // LOAM-iVox: every point the iVox map holds, voxels in LRU order
+        r->p2p->ivox().dump(iv);
+        m = &iv;
+    }
     if (r->icp) m = &r->icp->map();
     else if (r->kd) m = &r->kd->map();
     else if (r->full) m = which ? &r->full->corner_map() : &r->full->planar_map();

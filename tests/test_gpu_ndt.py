@@ -85,3 +85,30 @@ def test_streaming_mapping_mode(world, traj):
         assert dt < POS_TOL and dr < ROT_TOL, (k, dt, dr)
         assert g.map_info().n_voxels == o.map_voxels, k
     assert synth.pose_error(Tg, traj[5])[0] < 0.05
+
+
+def test_batch_equals_single_and_oracle(world, traj, scene64):
+    """fls_match_batch for IncrementalNDT: one cooperative launch, a sub-grid and a Gauss-Newton loop per scan.  Every scan's
+    result must equal its own single Match (same arithmetic, different CTA count -> fp64 rounding only) and the oracle."""
+    cfg = default_config(FLS_NDT)
+    g, o = _pair(cfg)
+    g.AddCloudToLocalMap([scene64["map"]])
+    o.add_cloud(scene64["map"])
+    scans, guesses = [], []
+    for k in range(5):
+        sensor = "hdl64" if k % 2 == 0 else "vlp16"  # ragged batch: different sizes -> different sub-grids
+        scans.append(synth.make_scan(world, traj[2 + k], sensor, seed=70 + k)["points"])
+        guesses.append(synth.perturb_pose(traj[2 + k], seed=700 + k, dpos=0.05, drot_deg=0.5))
+    oks, Ts = g.match_batch(scans, np.stack(guesses))
+    sts = g.last_batch_stats
+    for k in range(5):
+        T1 = guesses[k].copy()
+        ok1 = g.Match(_cluster(scans[k]), T1)
+        ok_o, To, st_o = o.match(scans[k], guesses[k])
+        assert bool(oks[k]) == ok1 == ok_o, k
+        assert sts[k].iterations == g.last_stats.iterations == st_o.iterations, k
+        assert sts[k].n_valid == g.last_stats.n_valid == st_o.n_valid, k
+        dt, dr = synth.pose_error(Ts[k], T1)
+        assert dt < 1e-9 and dr < 1e-9, (k, dt, dr)
+        dt, dr = synth.pose_error(Ts[k], To)
+        assert dt < POS_TOL and dr < ROT_TOL, (k, dt, dr)
