@@ -944,8 +944,28 @@ int fls_project(int device, const void* raw, const int32_t* ring, size_t n, size
         return FLS_ERR_INVALID_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return FLS_ERR_NO_DEVICE;
-    return fls::project_device(device, raw, ring, n, stride, n_rows, n_cols, horizontal_resolution, min_distance, max_distance, ordered, depth, col,
-                               row_start, row_end, n_ordered);
+    return fls::project_device(device, raw, ring, nullptr, nullptr, n, stride, n_rows, n_cols, horizontal_resolution, min_distance, max_distance, ordered,
+                               depth, col, row_start, row_end, n_ordered);
+}
+
+int fls_project_imu(int device, const void* raw, const int32_t* ring, const float* time, size_t n, size_t stride, const fls_imu_buffer* imu,
+                    int32_t n_rows, int32_t n_cols, float horizontal_resolution, float min_distance, float max_distance, float* ordered, float* depth,
+                    int32_t* col, int32_t* row_start, int32_t* row_end, size_t* n_ordered) {
+    if ((!raw && n) || (!ring && n) || !ordered || !depth || !col || !row_start || !row_end || !n_ordered || !stride_ok(stride))
+        return FLS_ERR_INVALID_ARG;
+    if (imu && imu->n_imu && !time && n) return FLS_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return FLS_ERR_NO_DEVICE;
+    return fls::project_device(device, raw, ring, time, imu, n, stride, n_rows, n_cols, horizontal_resolution, min_distance, max_distance, ordered,
+                               depth, col, row_start, row_end, n_ordered);
+}
+
+int fls_preprocess(int device, const float* raw_xyzit, size_t n, const fls_imu_buffer* imu, float min_distance, float max_distance, int32_t jump_span,
+                   float planar_leaf, float* ordered, size_t* n_ordered, float* planar, size_t* n_planar) {
+    if ((!raw_xyzit && n) || !ordered || !planar || !n_ordered || !n_planar || jump_span < 1 || !(planar_leaf > 0.f)) return FLS_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return FLS_ERR_NO_DEVICE;
+    return fls::preprocess_device(device, raw_xyzit, n, imu, min_distance, max_distance, jump_span, planar_leaf, ordered, n_ordered, planar, n_planar);
 }
 
 const char* fls_strerror(int status) {

@@ -155,8 +155,12 @@ int extract_features_device(int device, const float* depth, const int* col, size
                             fls_match_stats* stats);
 
 // repack caller records (stride >= 20, intensity at byte 16) into packed float4 on the device
-int project_device(int device, const void* raw, const int* ring, size_t n, size_t stride, int V, int H, float h_res, float min_d, float max_d,
-                   float* ordered_out, float* depth_out, int* col_out, int* row_start, int* row_end, size_t* n_out);
+int project_device(int device, const void* raw, const int* ring, const float* time, const fls_imu_buffer* imu, size_t n, size_t stride, int V, int H,
+                   float h_res, float min_d, float max_d, float* ordered_out, float* depth_out, int* col_out, int* row_start, int* row_end,
+                   size_t* n_out);
+// PreProcessing::Run, non-feature branch (preprocessing.cpp:181-225): raw x,y,z,intensity,time records -> ordered + planar clouds (host)
+int preprocess_device(int device, const float* raw_xyzit, size_t n, const fls_imu_buffer* imu, float min_d, float max_d, int jump_span, float leaf,
+                      float* ordered_out, size_t* n_ordered, float* planar_out, size_t* n_planar);
 void launch_repack(const unsigned char* d_raw, size_t n, size_t stride, float4* d_out, cudaStream_t st);
 // TransformPointCloud(cloud, Mat4d) with R, t cast to float first (pointcloud_utility.h:141-158 upstream); T column-major
 void launch_transform_f(const float4* d_in, size_t n, const double* T_colmajor, float4* d_out, cudaStream_t st);

@@ -5,12 +5,13 @@
 //
 // The sequential "first point to reach a cell keeps it" (:90-91) becomes an atomicMin on the point's position in the
 // raw cloud: the smallest index is by definition the first one the sequential loop would have seen.  The per-point
-// de-skew (ProcessPoint, :100-103) needs the IMU pose buffer and is outside this library's scope: points
-// pass through unchanged, as in the oracle.
+// de-skew (ProcessPoint, :100-103) runs on the winner of every cell when the caller passes the IMU orientation buffer
+// (fls_project_imu; fls_deskew.cuh); without one the points pass through unchanged.
 #include <cub/cub.cuh>
 
 #include <mutex>
 
+#include "fls_deskew.cuh"
 #include "fls_maps.h"
 
 namespace fls {
@@ -46,8 +47,8 @@ __global__ void proj_clear_kernel(unsigned* __restrict__ winner, size_t cells) {
     if (i < cells) winner[i] = 0xffffffffu;
 }
 
-__global__ void proj_claim_kernel(const float4* __restrict__ raw, const int* __restrict__ ring, int n, int V, int H, float h_res, float min_d,
-                                  float max_d, unsigned* __restrict__ winner) {
+__global__ void proj_claim_kernel(const float4* __restrict__ raw, const int* __restrict__ ring, const float* __restrict__ time, DeskewView dv, int n,
+                                  int V, int H, float h_res, float min_d, float max_d, unsigned* __restrict__ winner) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const float4 p = raw[k];
@@ -57,6 +58,10 @@ __global__ void proj_claim_kernel(const float4* __restrict__ raw, const int* __r
     int col = (int)roundf(__fdiv_rn(fast_atan2_ref(p.y, p.x), h_res)) + H / 2;  // :64-65
     if (col >= H) col -= H;
     if (row >= V || row < 0 || col < 0 || col >= H) return;  // :81-82
+    if (dv.m > 0) {  // ProcessPoint fails for a time outside the IMU buffer: the point returns without claiming its cell (:100-103)
+        const unsigned long long t = (unsigned long long)((long long)dv.ref_time + (long long)__dmul_rn((double)time[k], 1.0e6));
+        if (dv.m < 2 || dv.t[0] > t || dv.t[dv.m - 1] < t) return;
+    }
     atomicMin(&winner[(size_t)row * H + col], (unsigned)k);  // :86-87 first hit wins
 }
 
@@ -65,7 +70,8 @@ __global__ void proj_flags_kernel(const unsigned* __restrict__ winner, size_t ce
     if (i < cells) flag[i] = winner[i] != 0xffffffffu ? 1u : 0u;
 }
 
-__global__ void proj_emit_kernel(const float4* __restrict__ raw, const unsigned* __restrict__ winner, const unsigned* __restrict__ excl, int V, int H,
+__global__ void proj_emit_kernel(const float4* __restrict__ raw, const float* __restrict__ time, DeskewView dv, const unsigned* __restrict__ winner,
+                                 const unsigned* __restrict__ excl, int V, int H,
                                  float4* __restrict__ ordered, float* __restrict__ depth, int* __restrict__ col, int* __restrict__ row_start,
                                  int* __restrict__ row_end, unsigned* __restrict__ total) {
     const size_t cells = (size_t)V * H;
@@ -75,7 +81,9 @@ __global__ void proj_emit_kernel(const float4* __restrict__ raw, const unsigned*
     const unsigned pos = excl[i];
     if (w != 0xffffffffu) {
         const float4 p = raw[w];
-        ordered[pos] = p;
+        float4 q = p;
+        if (dv.m > 0) deskew_point(dv, p.x, p.y, p.z, time[w], q.x, q.y, q.z);  // :100-103; the range stays the raw point's (:57, :105)
+        ordered[pos] = q;
         depth[pos] = depth_ref(p.x, p.y, p.z);
         col[pos] = (int)(i % (size_t)H);
     }
@@ -96,7 +104,9 @@ struct ProjWorkspace {
     DevBuf<unsigned char> staging;
     DevBuf<int> ring, col, rows;
     DevBuf<unsigned> winner, flag, excl, total;
-    DevBuf<float> depth;
+    DevBuf<float> depth, time;
+    DevBuf<unsigned long long> imu_t;
+    DevBuf<double> imu_q;
     DevBuf<unsigned char> cub_tmp;
 };
 ProjWorkspace& proj_workspace(int device) {
@@ -108,8 +118,10 @@ ProjWorkspace& proj_workspace(int device) {
 
 // Host driver: raw cloud (host, `stride` bytes per record) + ring per point -> projector arrays (host).  depth_out / col_out hold V*H
 // entries (the first *n_out are meaningful, as upstream), ordered_out V*H packed float4 records.
-int project_device(int device, const void* raw, const int* ring, size_t n, size_t stride, int V, int H, float h_res, float min_d, float max_d,
-                   float* ordered_out, float* depth_out, int* col_out, int* row_start, int* row_end, size_t* n_out) {
+int make_deskew_view(const fls_imu_buffer* imu, DevBuf<unsigned long long>& d_t, DevBuf<double>& d_q, cudaStream_t st, DeskewView& v);
+
+int project_device(int device, const void* raw, const int* ring, const float* time, const fls_imu_buffer* imu, size_t n, size_t stride, int V, int H,
+                   float h_res, float min_d, float max_d, float* ordered_out, float* depth_out, int* col_out, int* row_start, int* row_end, size_t* n_out) {
     *n_out = 0;
     if (V <= 0 || H <= 0 || !(h_res > 0.f) || device < 0 || device >= 64 || n > 0x7fffffffull) return FLS_ERR_INVALID_ARG;
     const size_t cells = (size_t)V * H;
@@ -124,8 +136,17 @@ int project_device(int device, const void* raw, const int* ring, size_t n, size_
             w.ready = true;
         }
         cudaStream_t st = w.st;
+        DeskewView dv;
+        const bool use_imu = imu && imu->n_imu && time;
+        rc = make_deskew_view(use_imu ? imu : nullptr, w.imu_t, w.imu_q, st, dv);
+        const bool ref_failed = rc == FLS_ERR_INVALID_ARG && use_imu && imu->imu_time_us && imu->imu_quat_xyzw;  // SetRefTime failed: no point is accepted
+        if (rc != FLS_OK && !ref_failed) return rc;
+        rc = FLS_OK;
+        if (ref_failed) n = 0;
         w.raw.reserve(n + 1);
         w.ring.reserve(n + 1);
+        w.time.reserve(n + 1);
+        if (n && use_imu) FLS_CUDA(cudaMemcpyAsync(w.time.p, time, n * sizeof(float), cudaMemcpyHostToDevice, st));
         w.winner.reserve(cells);
         w.flag.reserve(cells);
         w.excl.reserve(cells);
@@ -146,7 +167,7 @@ int project_device(int device, const void* raw, const int* ring, size_t n, size_
         }
         const unsigned gc = (unsigned)((cells + 255) / 256);
         proj_clear_kernel<<<gc, 256, 0, st>>>(w.winner.p, cells);
-        if (n) proj_claim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.raw.p, w.ring.p, (int)n, V, H, h_res, min_d, max_d, w.winner.p);
+        if (n) proj_claim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.raw.p, w.ring.p, w.time.p, dv, (int)n, V, H, h_res, min_d, max_d, w.winner.p);
         proj_flags_kernel<<<gc, 256, 0, st>>>(w.winner.p, cells, w.flag.p);
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, w.flag.p, w.excl.p, (int)cells, st);
@@ -156,7 +177,7 @@ int project_device(int device, const void* raw, const int* ring, size_t n, size_
         // upstream leaves the tails of depth / col as they were (resize to V*H, col zero-filled): zero both
         FLS_CUDA(cudaMemsetAsync(w.depth.p, 0, cells * sizeof(float), st));
         FLS_CUDA(cudaMemsetAsync(w.col.p, 0, cells * sizeof(int), st));
-        proj_emit_kernel<<<gc, 256, 0, st>>>(w.raw.p, w.winner.p, w.excl.p, V, H, w.ordered.p, w.depth.p, w.col.p, w.rows.p, w.rows.p + V, w.total.p);
+        proj_emit_kernel<<<gc, 256, 0, st>>>(w.raw.p, w.time.p, dv, w.winner.p, w.excl.p, V, H, w.ordered.p, w.depth.p, w.col.p, w.rows.p, w.rows.p + V, w.total.p);
         FLS_CUDA(cudaGetLastError());
         unsigned total = 0;
         FLS_CUDA(cudaMemcpyAsync(&total, w.total.p, sizeof(total), cudaMemcpyDeviceToHost, st));

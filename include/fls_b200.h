@@ -14,7 +14,9 @@
  *   fls_fitness                <- RegistrationInterface::GetFitnessScore (registration_interface.h:19)
  *   fls_extract_features       <- loam::FeatureExtractor::ExtractFeatures
  *                                 (include/loam/feature_extractor.h:22, src/loam/feature_extractor.cpp:35-44)
- *   fls_project                <- loam::PointcloudProjector::Project (src/loam/pointcloud_projector.cpp:32-133)
+ *   fls_project / _imu         <- loam::PointcloudProjector::Project (src/loam/pointcloud_projector.cpp:32-133)
+ *   fls_preprocess             <- PreProcessing::Run range gate + LidarDistortionCorrector::ProcessPoint + jump span + VoxelGrid
+ *                                 (src/slam/preprocessing.cpp:181-225, src/lidar/lidar_distortion_corrector.cpp:37-64)
  *   fls_voxel_grid             <- VoxelGridCloud (include/common/pointcloud_utility.h:216-224,263-271)
  *
  * Conventions
@@ -228,11 +230,38 @@ int fls_extract_features(const fls_feature_cfg* cfg, const float* depth, const i
 
 /* PointcloudProjector::Project (src/loam/pointcloud_projector.cpp:32-133): raw cloud + ring per point (firing order) ->
  * ordered_cloud_ (packed float4, capacity n_rows*n_cols), point_depth_vec_ / point_col_index_vec_ (n_rows*n_cols entries, the
- * first *n_ordered meaningful), row_start_index_vec_ / row_end_index_vec_ (n_rows).  The IMU de-skew of :100-103 is not
- * applied (identity) — it depends on the pose buffer of the caller. */
+ * first *n_ordered meaningful), row_start_index_vec_ / row_end_index_vec_ (n_rows).  Without an IMU buffer the de-skew of :100-103
+ * is the identity; fls_project_imu below applies it. */
 int fls_project(int device, const void* raw, const int32_t* ring, size_t n, size_t stride_bytes, int32_t n_rows, int32_t n_cols,
                 float horizontal_resolution, float min_distance, float max_distance, float* ordered, float* depth, int32_t* col,
                 int32_t* row_start, int32_t* row_end, size_t* n_ordered);
+
+/* IMU orientation samples around a scan — what LidarDistortionCorrector reads through its DataSearcher<IMUData>
+ * (include/lidar/lidar_distortion_corrector.h:11-48, src/lidar/lidar_distortion_corrector.cpp:19-64): time stamps in microseconds
+ * (ascending), unit quaternions in Eigen coefficient order x, y, z, w, the reference time of the scan (SetRefTime) and the
+ * lidar -> imu extrinsic (column-major 4x4).  n_imu == 0 (or a NULL pointer to the struct): no de-skew, points pass unchanged. */
+typedef struct {
+    const uint64_t* imu_time_us;
+    const double* imu_quat_xyzw;
+    size_t n_imu;
+    uint64_t ref_time_us;
+    double T_lidar_to_imu[16];
+} fls_imu_buffer;
+
+/* PreProcessing::Run, the branch of the plug-ins that take no features (src/slam/preprocessing.cpp:181-225): per raw point
+ * {x, y, z, intensity, time-relative-to-ref [s]} (5 floats, firing order): range gate [min_distance, max_distance], IMU de-skew
+ * (a point whose time is outside the IMU buffer is dropped), ordered_cloud_ = every kept point, planar_cloud_ = the kept points
+ * whose RAW index is a multiple of jump_span, then pcl::VoxelGrid(planar_leaf).  Outputs: packed x, y, z, intensity records,
+ * each buffer with room for n points.  When ref_time_us is outside the IMU buffer upstream skips the scan: both counts are 0. */
+int fls_preprocess(int device, const float* raw_xyzit, size_t n, const fls_imu_buffer* imu, float min_distance, float max_distance,
+                   int32_t jump_span, float planar_leaf, float* ordered, size_t* n_ordered, float* planar, size_t* n_planar);
+
+/* fls_project with the per-point de-skew of pointcloud_projector.cpp:100-103: `time` holds the time of every raw point relative to
+ * ref_time_us [s].  A point whose time is outside the IMU buffer does not claim its cell; the depth of a cell stays the range of
+ * the raw point (:57, :105). */
+int fls_project_imu(int device, const void* raw, const int32_t* ring, const float* time, size_t n, size_t stride_bytes, const fls_imu_buffer* imu,
+                    int32_t n_rows, int32_t n_cols, float horizontal_resolution, float min_distance, float max_distance, float* ordered,
+                    float* depth, int32_t* col, int32_t* row_start, int32_t* row_end, size_t* n_ordered);
 
 const char* fls_strerror(int status);
 const char* fls_last_error(void); /* thread-local text of the last CUDA failure */

@@ -14,6 +14,7 @@
 
 #include "../include/fls_b200.h"
 #include "orc_cloud.h"
+#include "orc_deskew.h"
 #include "orc_features.h"
 #include "orc_ivox.h"
 #include "orc_math.h"
@@ -309,6 +310,42 @@ size_t orc_reg_ndt_dump(void* h, int* keys, double* mu, double* info, int* est) 
     std::memcpy(info, i.data(), i.size() * sizeof(double));
     std::memcpy(est, e.data(), e.size() * sizeof(int));
     return e.size();
+}
+
+// ---- pre-hot-path pipeline: range gate + IMU de-skew + jump span + voxel filter; projector with de-skew -------------------------
+static ImuBuffer make_imu(const uint64_t* t, const double* q_xyzw, size_t m, uint64_t ref_time, const double* T_li) {
+    ImuBuffer b;
+    b.t.assign(t, t + m);
+    b.q.resize(m);
+    for (size_t i = 0; i < m; ++i) b.q[i] = Quat{q_xyzw[4 * i], q_xyzw[4 * i + 1], q_xyzw[4 * i + 2], q_xyzw[4 * i + 3]};
+    b.ref_time = ref_time;
+    std::memcpy(b.T_li, T_li, sizeof(b.T_li));
+    return b;
+}
+// returns n_ordered; *n_planar set; outputs sized n (packed xyzi)
+size_t orc_preprocess(const float* raw_xyzit, size_t n, const uint64_t* imu_t, const double* imu_q, size_t m, uint64_t ref_time, const double* T_li,
+                      float min_d, float max_d, int jump_span, float leaf, float* ordered, float* planar, size_t* n_planar) {
+    ImuBuffer b;
+    if (imu_t) b = make_imu(imu_t, imu_q, m, ref_time, T_li);
+    const Preprocessed p = preprocess(raw_xyzit, n, imu_t ? &b : nullptr, min_d, max_d, jump_span, leaf);
+    std::memcpy(ordered, p.ordered.data(), p.ordered.size() * sizeof(P4));
+    std::memcpy(planar, p.planar.data(), p.planar.size() * sizeof(P4));
+    *n_planar = p.planar.size();
+    return p.ordered.size();
+}
+size_t orc_project_imu(const float* raw, const int* ring, const float* time, size_t n, const uint64_t* imu_t, const double* imu_q, size_t m,
+                       uint64_t ref_time, const double* T_li, int V, int H, float h_res, float min_d, float max_d, float* ordered, float* depth,
+                       int* col, int* row_start, int* row_end) {
+    std::vector<int> rg(ring, ring + n);
+    ImuBuffer b;
+    if (imu_t) b = make_imu(imu_t, imu_q, m, ref_time, T_li);
+    const Projected p = project_imu(load_cloud(raw, n, 16), rg, time, imu_t ? &b : nullptr, V, H, h_res, min_d, max_d);
+    std::memcpy(ordered, p.ordered.data(), p.ordered.size() * sizeof(P4));
+    std::memcpy(depth, p.depth.data(), p.depth.size() * sizeof(float));
+    std::memcpy(col, p.col.data(), p.col.size() * sizeof(int));
+    std::memcpy(row_start, p.row_start.data(), V * sizeof(int));
+    std::memcpy(row_end, p.row_end.data(), V * sizeof(int));
+    return p.ordered.size();
 }
 
 // ---- LOAM features ----------------------------------------------------------------------------------

@@ -73,6 +73,10 @@ def lib():
         L.orc_reg_ndt_dump.argtypes = [vp, vp, vp, vp, vp]
         L.orc_project.restype = sz
         L.orc_project.argtypes = [vp, vp, sz, i32, i32, f32, f32, f32, vp, vp, vp, vp, vp]
+        L.orc_preprocess.restype = sz
+        L.orc_preprocess.argtypes = [vp, sz, vp, vp, sz, C.c_uint64, vp, f32, f32, i32, f32, vp, vp, C.POINTER(sz)]
+        L.orc_project_imu.restype = sz
+        L.orc_project_imu.argtypes = [vp, vp, vp, sz, vp, vp, sz, C.c_uint64, vp, i32, i32, f32, f32, f32, vp, vp, vp, vp, vp]
         L.orc_extract_features.argtypes = [vp, vp, sz, vp, vp, i32, f32, f32, vp, C.POINTER(sz), vp, C.POINTER(sz), C.POINTER(dbl)]
         _lib = L
     return _lib
@@ -310,6 +314,45 @@ def project(raw, ring, V, H, h_res, min_d, max_d):
     rs = np.zeros(V, np.int32)
     re = np.zeros(V, np.int32)
     n = lib().orc_project(_p(raw), _p(ring), len(raw), V, H, float(h_res), float(min_d), float(max_d), _p(ordered), _p(depth), _p(col), _p(rs), _p(re))
+    return dict(ordered=ordered[:n].copy(), depth=depth, col=col, row_start=rs, row_end=re, n=n)
+
+
+def _imu_args(imu):
+    if imu is None:
+        return None, None, 0, 0, _p(np.eye(4).T.copy()), ()
+    t = np.ascontiguousarray(imu["t_us"], np.uint64)
+    q = np.ascontiguousarray(imu["q_xyzw"], np.float64)
+    T = np.ascontiguousarray(np.asarray(imu["T_lidar_to_imu"], np.float64).T)  # column-major
+    return _p(t), _p(q), len(t), int(imu["ref_time_us"]), _p(T), (t, q, T)
+
+
+def preprocess(raw_xyzit, imu, min_d, max_d, jump_span, leaf):
+    """preprocessing.cpp:181-225 (non-feature branch): range gate + IMU de-skew + jump span + voxel filter.
+    raw_xyzit: (n,5) float32 x,y,z,intensity,relative time [s]; imu: dict(t_us, q_xyzw, ref_time_us, T_lidar_to_imu) or None."""
+    raw = np.ascontiguousarray(raw_xyzit, np.float32)
+    n = len(raw)
+    ordered = np.zeros((max(n, 1), 4), np.float32)
+    planar = np.zeros((max(n, 1), 4), np.float32)
+    npl = C.c_size_t(0)
+    pt, pq, m, ref, pT, keep = _imu_args(imu)
+    no = lib().orc_preprocess(_p(raw), n, pt, pq, m, ref, pT, float(min_d), float(max_d), int(jump_span), float(leaf), _p(ordered), _p(planar),
+                              C.byref(npl))
+    return ordered[:no].copy(), planar[:npl.value].copy()
+
+
+def project_imu(raw, ring, time, imu, V, H, h_res, min_d, max_d):
+    """pointcloud_projector.cpp:32-133 with the per-point de-skew of :100-103."""
+    raw = _f4(raw)
+    ring = np.ascontiguousarray(ring, np.int32)
+    time = np.ascontiguousarray(time, np.float32)
+    ordered = np.zeros((V * H, 4), np.float32)
+    depth = np.zeros(V * H, np.float32)
+    col = np.zeros(V * H, np.int32)
+    rs = np.zeros(V, np.int32)
+    re = np.zeros(V, np.int32)
+    pt, pq, m, ref, pT, keep = _imu_args(imu)
+    n = lib().orc_project_imu(_p(raw), _p(ring), _p(time), len(raw), pt, pq, m, ref, pT, V, H, float(h_res), float(min_d), float(max_d), _p(ordered),
+                              _p(depth), _p(col), _p(rs), _p(re))
     return dict(ordered=ordered[:n].copy(), depth=depth, col=col, row_start=rs, row_end=re, n=n)
 
 
