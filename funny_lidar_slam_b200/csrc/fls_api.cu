@@ -180,6 +180,13 @@ int Handle::add_cloud_ivox(const void* pts, size_t n, size_t stride) {
 // The whole LoamPointToPlaneIVOX Match of `n_scans` independent scans in one persistent launch (K1, fls_p2plane.cu).
 // A single Match is the batch of one.
 int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* n, double* T, int* converged, fls_match_stats* st) {
+    const int rc = enqueue_ivox_batch(B, d_scans, n, T);
+    if (rc != FLS_OK) return rc;
+    return finish_ivox_batch(T, converged, st);
+}
+
+// everything of a batch up to the asynchronous read-back of the states: nothing here waits for the device
+int Handle::enqueue_ivox_batch(int B, const float4* const* d_scans, const size_t* n, const double* T) {
     if (ivox.n_pts == 0) return FLS_ERR_NO_MAP;
     if (B < 1 || B > kMaxBatch) return FLS_ERR_INVALID_ARG;
     int off[kMaxBatch + 1];
@@ -312,6 +319,17 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
         FLS_CUDA(cudaMemcpyAsync(h_log.data(), log.p, sizeof(fls_iter_log) * log_cap, cudaMemcpyDeviceToHost, stream));
         d2h_bytes += (long long)(sizeof(fls_iter_log) * log_cap);
     }
+    pend_n.assign(n, n + B);
+    pend_v9 = use_v9;
+    return FLS_OK;
+}
+
+// waits for the batch enqueued last and unpacks its results
+int Handle::finish_ivox_batch(double* T, int* converged, fls_match_stats* st) {
+    const int B = (int)pend_n.size();
+    if (B < 1) return FLS_ERR_INVALID_ARG;
+    const size_t* n = pend_n.data();
+    const bool use_v9 = pend_v9;
     end_call(st);
     float kernel_ms = 0.f;
     if (profile) FLS_CUDA(cudaEventElapsedTime(&kernel_ms, prof_ev[0], prof_ev[1]));
@@ -344,6 +362,7 @@ int Handle::match_ivox_batch(int B, const float4* const* d_scans, const size_t* 
     }
     std::memcpy(T_final, T, sizeof(T_final));
     log_n = h_state[0].iter < log_cap ? h_state[0].iter : log_cap;
+    pend_n.clear();
     if (std::getenv("FLS_DEBUG_TIMING")) {
         const GnState& g0 = h_state[0];
         std::fprintf(stderr, "[fls timing] batch %d  scan 0: iters %d  candidates/pt-iter %.1f\n", B, g0.iter,
@@ -1203,6 +1222,68 @@ int fls_match_batch(fls_handle* hh, int n_scans, const void* const* planar, cons
     if (h->cfg.method == FLS_NDT) return n_scans == 1 ? h->match_ndt(ptrs[0], n[0], T, converged, st) : h->match_ndt_batch(n_scans, ptrs, n, T, converged, st);
     if (n_scans == 1) return h->match_p2plane_ivox(ptrs[0], n[0], T, converged, st);
     return h->match_ivox_batch(n_scans, ptrs, n, T, converged, st);
+    FLS_CATCH
+}
+
+int fls_match_batch_begin(fls_handle* hh, int n_scans, const void* const* planar, const size_t* n, size_t stride, const double* T) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || !planar || !n || !T || n_scans < 1 || n_scans > fls::kMaxBatch || !stride_ok(stride)) return FLS_ERR_INVALID_ARG;
+    if (h->cfg.method != FLS_P2PLANE_IVOX) return FLS_ERR_UNSUPPORTED;
+    if (!h->cfg.localization_mode) return FLS_ERR_UNSUPPORTED;  // the map must not change between begin and end
+    if (!h->pend_n.empty()) return FLS_ERR_INVALID_ARG;         // one batch in flight per handle
+    FLS_TRY
+    h->begin_call();
+    size_t total = 0;
+    for (int s = 0; s < n_scans; ++s) {
+        if (!planar[s] && n[s]) return FLS_ERR_INVALID_ARG;
+        total += n[s];
+    }
+    h->src.reserve(total + 1);
+    if (stride != FLS_LAYOUT_PACKED) h->raw.reserve(total * stride);
+    const float4* ptrs[fls::kMaxBatch];
+    size_t off = 0;
+    for (int s = 0; s < n_scans; ++s) {
+        ptrs[s] = h->src.p + off;
+        if (n[s]) {
+            if (stride == FLS_LAYOUT_PACKED) {
+                FLS_CUDA(cudaMemcpyAsync(h->src.p + off, planar[s], n[s] * 16, cudaMemcpyHostToDevice, h->stream));
+            } else {
+                FLS_CUDA(cudaMemcpyAsync(h->raw.p + off * stride, planar[s], n[s] * stride, cudaMemcpyHostToDevice, h->stream));
+                fls::launch_repack(h->raw.p + off * stride, n[s], stride, h->src.p + off, h->stream);
+                h->launches++;
+            }
+            h->h2d_bytes += (long long)(n[s] * stride);
+        }
+        off += n[s];
+    }
+    return h->enqueue_ivox_batch(n_scans, ptrs, n, T);
+    FLS_CATCH
+}
+
+int fls_match_batch_begin_device(fls_handle* hh, int n_scans, const void* const* d_planar, const size_t* n, const double* T) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || !d_planar || !n || !T || n_scans < 1 || n_scans > fls::kMaxBatch) return FLS_ERR_INVALID_ARG;
+    if (h->cfg.method != FLS_P2PLANE_IVOX) return FLS_ERR_UNSUPPORTED;
+    if (!h->cfg.localization_mode) return FLS_ERR_UNSUPPORTED;
+    if (!h->pend_n.empty()) return FLS_ERR_INVALID_ARG;
+    FLS_TRY
+    h->begin_call();
+    const float4* ptrs[fls::kMaxBatch];
+    for (int s = 0; s < n_scans; ++s) {
+        if (!d_planar[s] && n[s]) return FLS_ERR_INVALID_ARG;
+        ptrs[s] = static_cast<const float4*>(d_planar[s]);
+    }
+    return h->enqueue_ivox_batch(n_scans, ptrs, n, T);
+    FLS_CATCH
+}
+
+int fls_match_batch_end(fls_handle* hh, double* T, int* converged, fls_match_stats* st) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || !T) return FLS_ERR_INVALID_ARG;
+    if (h->pend_n.empty()) return FLS_ERR_INVALID_ARG;
+    FLS_TRY
+    if (st) std::memset(st, 0, sizeof(*st) * h->pend_n.size());
+    return h->finish_ivox_batch(T, converged, st);
     FLS_CATCH
 }
 

@@ -109,6 +109,11 @@ struct Handle {
     int match_p2plane_ivox(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st);
     // n_scans independent scans against the (static) map in ONE persistent launch; d_scans: host array of device pointers
     int match_ivox_batch(int n_scans, const float4* const* d_scans, const size_t* n, double* T, int* converged, fls_match_stats* st);
+    // the same in two halves (fls_match_batch_begin / _end): enqueue without waiting, then wait + unpack
+    int enqueue_ivox_batch(int n_scans, const float4* const* d_scans, const size_t* n, const double* T);
+    int finish_ivox_batch(double* T, int* converged, fls_match_stats* st);
+    std::vector<size_t> pend_n;  // scans of the batch in flight (empty: none)
+    bool pend_v9 = false;
 
     int add_cloud_ndt(const float4* d_cloud, size_t n);
     int match_ndt(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st);

@@ -115,6 +115,44 @@ class Registration:
         self.last_stats = st[0]
         return np.array(conv[:], bool), np.transpose(Tc, (0, 2, 1)).copy()
 
+    def match_batch_begin(self, scans, Ts) -> None:
+        """First half of match_batch: enqueue copies + matching + read-back on the handle's stream, do not wait (the scans should sit
+        in pinned host memory).  With two handles the copy of one batch overlaps the kernels of the other."""
+        B = len(scans)
+        ptrs, ns, keep, stride = [], [], [], None
+        for c in scans:
+            p, n, s, a = _cloud(c)
+            if stride is not None and s != stride:
+                raise ValueError("all scans of one batch must share a layout")
+            stride = s
+            ptrs.append(p)
+            ns.append(n)
+            keep.append(a)
+        Tc = np.ascontiguousarray(np.transpose(np.asarray(Ts, np.float64), (0, 2, 1))).copy()
+        arr_p = (C.c_void_p * B)(*ptrs)
+        arr_n = (C.c_size_t * B)(*ns)
+        self._pending = (keep, arr_p, arr_n, Tc, B)
+        check(lib().fls_match_batch_begin(self._h, B, arr_p, arr_n, stride, Tc.ctypes.data_as(C.c_void_p)), "fls_match_batch_begin")
+
+    def match_batch_begin_device(self, d_ptrs, ns, Ts) -> None:
+        """match_batch_begin with device-resident packed float4 scans."""
+        B = len(d_ptrs)
+        Tc = np.ascontiguousarray(np.transpose(np.asarray(Ts, np.float64), (0, 2, 1))).copy()
+        arr_p = (C.c_void_p * B)(*[int(p) for p in d_ptrs])
+        arr_n = (C.c_size_t * B)(*[int(n) for n in ns])
+        self._pending = ((), arr_p, arr_n, Tc, B)
+        check(lib().fls_match_batch_begin_device(self._h, B, arr_p, arr_n, Tc.ctypes.data_as(C.c_void_p)), "fls_match_batch_begin_device")
+
+    def match_batch_end(self):
+        keep, arr_p, arr_n, Tc, B = self._pending
+        conv = (C.c_int * B)()
+        st = (FlsMatchStats * B)()
+        check(lib().fls_match_batch_end(self._h, Tc.ctypes.data_as(C.c_void_p), conv, st), "fls_match_batch_end")
+        self._pending = None
+        self.last_batch_stats = list(st)
+        self.last_stats = st[0]
+        return np.array(conv[:], bool), np.transpose(Tc, (0, 2, 1)).copy()
+
     def match_batch_device(self, d_ptrs, ns, Ts):
         """Same with device-resident packed float4 scans: d_ptrs = list of device addresses, ns = point counts."""
         B = len(d_ptrs)

@@ -182,6 +182,13 @@ int fls_fitness(fls_handle* h, float max_range, float* score);
  * Results are identical to n_scans separate fls_match calls.  The _device variant takes device pointers to packed float4 scans. */
 int fls_match_batch(fls_handle* h, int n_scans, const void* const* planar, const size_t* n, size_t stride_bytes, double* T_colmajor,
                     int* converged, fls_match_stats* stats);
+/* fls_match_batch in two halves, so that a caller with two handles overlaps the host->device copy of one batch with the kernels of
+ * the other: _begin enqueues the copies, the matching and the read-back on the handle's stream and returns without waiting (the
+ * host buffers — pinned, to be asynchronous — and `n` must stay valid until _end); _end waits and fills T / converged / stats like
+ * fls_match_batch.  FLS_P2PLANE_IVOX in localization mode; one batch in flight per handle. */
+int fls_match_batch_begin(fls_handle* h, int n_scans, const void* const* planar, const size_t* n, size_t stride_bytes, const double* T_colmajor);
+int fls_match_batch_begin_device(fls_handle* h, int n_scans, const void* const* d_planar, const size_t* n, const double* T_colmajor);
+int fls_match_batch_end(fls_handle* h, double* T_colmajor, int* converged, fls_match_stats* stats);
 int fls_match_batch_device(fls_handle* h, int n_scans, const void* const* d_planar, const size_t* n, double* T_colmajor, int* converged,
                            fls_match_stats* stats);
 
