@@ -15,7 +15,8 @@ EXPORTS = [
     "fls_abi_version", "fls_device_count", "fls_last_error", "fls_strerror", "fls_config_default", "fls_create", "fls_destroy",
     "fls_add_cloud", "fls_match", "fls_match_device", "fls_fitness", "fls_get_iter_log", "fls_get_map_info", "fls_ivox_knn",
     "fls_voxel_grid", "fls_extract_features", "fls_project", "fls_match_batch", "fls_match_batch_device",
-    "fls_set_result_buffer_device", "fls_get_voxel_keys", "fls_get_map_points", "fls_ivox_add_points", "fls_preprocess", "fls_project_imu", "fls_match_batch_begin", "fls_match_batch_begin_device", "fls_match_batch_end",
+    "fls_set_result_buffer_device", "fls_get_voxel_keys", "fls_get_map_points", "fls_ivox_add_points", "fls_preprocess", "fls_project_imu", "fls_match_batch_begin", "fls_match_batch_begin_device", "fls_match_batch_end", "fls_set_global_map", "fls_update_local_map",
+    "fls_pcd_read", "fls_pcd_write",
 ]
 
 
@@ -54,6 +55,10 @@ def lib():
     L.fls_set_result_buffer_device.argtypes = [vp, vp, sz]
     L.fls_match_batch_begin.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz), sz, vp]
     L.fls_match_batch_begin_device.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz), vp]
+    L.fls_set_global_map.argtypes = [vp, vp, sz, sz]
+    L.fls_update_local_map.argtypes = [vp, vp, C.POINTER(C.c_int), C.POINTER(sz)]
+    L.fls_pcd_read.argtypes = [C.c_char_p, vp, sz, C.POINTER(sz)]
+    L.fls_pcd_write.argtypes = [C.c_char_p, vp, sz]
     L.fls_match_batch_end.argtypes = [vp, vp, C.POINTER(C.c_int), C.POINTER(FlsMatchStats)]
     L.fls_fitness.argtypes = [vp, f32, C.POINTER(f32)]
     L.fls_get_iter_log.argtypes = [vp, C.POINTER(FlsIterLog), C.c_int]

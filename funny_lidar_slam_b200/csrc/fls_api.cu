@@ -1331,6 +1331,51 @@ int fls_get_iter_log(const fls_handle* hh, fls_iter_log* out, int capacity) {
     return n;
 }
 
+int fls_set_global_map(fls_handle* hh, const void* pts, size_t n, size_t stride) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || (!pts && n) || !stride_ok(stride)) return FLS_ERR_INVALID_ARG;
+    FLS_TRY
+    h->begin_call();
+    const int rc = h->set_global_map(pts, n, stride);
+    h->end_call(nullptr);
+    return rc;
+    FLS_CATCH
+}
+
+int fls_update_local_map(fls_handle* hh, const double* T, int* updated, size_t* n_local) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || !T) return FLS_ERR_INVALID_ARG;
+    FLS_TRY
+    h->begin_call();
+    const int rc = h->update_local_map(T, updated, n_local);
+    h->end_call(nullptr);
+    return rc;
+    FLS_CATCH
+}
+
+int fls_pcd_read(const char* path, float* xyzi, size_t capacity, size_t* n) {
+    if (!path || !n || (capacity && !xyzi)) return FLS_ERR_INVALID_ARG;
+    std::vector<float> v;
+    std::string err;
+    const int rc = fls::pcd_read(path, v, err);
+    if (rc != FLS_OK) {
+        fls::set_last_error(err);
+        return rc;
+    }
+    *n = v.size() / 4;
+    const size_t m = *n < capacity ? *n : capacity;
+    if (m) std::memcpy(xyzi, v.data(), m * 16);
+    return FLS_OK;
+}
+
+int fls_pcd_write(const char* path, const float* xyzi, size_t n) {
+    if (!path || (!xyzi && n)) return FLS_ERR_INVALID_ARG;
+    std::string err;
+    const int rc = fls::pcd_write(path, xyzi, n, err);
+    if (rc != FLS_OK) fls::set_last_error(err);
+    return rc;
+}
+
 int fls_get_voxel_keys(fls_handle* hh, int32_t* keys_xyz, size_t capacity, size_t* n) {
     Handle* h = reinterpret_cast<Handle*>(hh);
     if (!h || !n || (capacity && !keys_xyz)) return FLS_ERR_INVALID_ARG;

@@ -129,6 +129,15 @@ struct Handle {
     bool need_add_cloud(const double* T, double* last_T, bool* have_last) const;
 
     int fitness(float max_range, float* score);
+
+    // localization-mode map path (fls_localmap.cu): resident global map, +-100 m crop around the pose when needed
+    DevBuf<float4> global_map;
+    size_t global_n = 0;
+    DevBuf<unsigned char> crop_keep;
+    double local_edge[6] = {0, 0, 0, 0, 0, 0};
+    bool have_edge = false;
+    int set_global_map(const void* pts, size_t n, size_t stride);
+    int update_local_map(const double* T_colmajor, int* updated, size_t* n_local);
 };
 
 }  // namespace fls

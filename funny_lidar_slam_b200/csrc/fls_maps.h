@@ -154,6 +154,10 @@ int extract_features_device(int device, const float* depth, const int* col, size
                             float corner_thr, float planar_thr, int* corner_idx, size_t* n_corner, int* planar_idx, size_t* n_planar,
                             fls_match_stats* stats);
 
+// PCD v0.7 files of x y z [intensity] clouds (fls_localmap.cu)
+int pcd_read(const char* path, std::vector<float>& xyzi, std::string& err);
+int pcd_write(const char* path, const float* xyzi, size_t n, std::string& err);
+
 // repack caller records (stride >= 20, intensity at byte 16) into packed float4 on the device
 int project_device(int device, const void* raw, const int* ring, const float* time, const fls_imu_buffer* imu, size_t n, size_t stride, int V, int H,
                    float h_res, float min_d, float max_d, float* ordered_out, float* depth_out, int* col_out, int* row_start, int* row_end,

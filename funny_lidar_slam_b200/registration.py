@@ -181,6 +181,18 @@ class Registration:
         self.last_stats = st
         return bool(conv.value)
 
+    # -- localization-mode map path (Localization::LoadLocalMap upstream) ---------------------------------
+    def set_global_map(self, cloud: np.ndarray) -> None:
+        p, n, s, keep = _cloud(cloud)
+        check(lib().fls_set_global_map(self._h, p, n, s), "fls_set_global_map")
+
+    def update_local_map(self, T: np.ndarray):
+        """Re-cut the +-100 m local map around T when needed and hand it to the plug-in; returns (updated, n_local_points)."""
+        Tc = np.ascontiguousarray(np.asarray(T, np.float64).T).copy()
+        upd, nl = C.c_int(0), C.c_size_t(0)
+        check(lib().fls_update_local_map(self._h, Tc.ctypes.data_as(C.c_void_p), C.byref(upd), C.byref(nl)), "fls_update_local_map")
+        return bool(upd.value), int(nl.value)
+
     # -- introspection ---------------------------------------------------------------------------------
     def map_points(self) -> np.ndarray:
         """(n, 4) float32 points of the LOAM-iVox map, insertion order."""
@@ -250,3 +262,19 @@ def voxel_grid(points: np.ndarray, leaf: float, device: int = 0) -> np.ndarray:
     n_out = C.c_size_t(0)
     check(lib().fls_voxel_grid(device, p, n, s, float(leaf), out.ctypes.data_as(C.c_void_p), C.byref(n_out)), "fls_voxel_grid")
     return out[:n_out.value].copy()
+
+
+def pcd_write(path: str, cloud: np.ndarray) -> None:
+    """pcl::io::savePCDFileBinary of an x y z intensity cloud."""
+    c = np.ascontiguousarray(cloud, np.float32)
+    assert c.ndim == 2 and c.shape[1] == 4
+    check(lib().fls_pcd_write(str(path).encode(), c.ctypes.data_as(C.c_void_p), len(c)), "fls_pcd_write")
+
+
+def pcd_read(path: str) -> np.ndarray:
+    """pcl::io::loadPCDFile into packed x y z intensity records."""
+    n = C.c_size_t(0)
+    check(lib().fls_pcd_read(str(path).encode(), None, 0, C.byref(n)), "fls_pcd_read")
+    out = np.zeros((max(n.value, 1), 4), np.float32)
+    check(lib().fls_pcd_read(str(path).encode(), out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "fls_pcd_read")
+    return out[:n.value]

@@ -243,6 +243,21 @@ int fls_project(int device, const void* raw, const int32_t* ring, size_t n, size
                 float horizontal_resolution, float min_distance, float max_distance, float* ordered, float* depth, int32_t* col,
                 int32_t* row_start, int32_t* row_end, size_t* n_ordered);
 
+/* Localization mode, the map side (Localization::LoadLocalMap, src/slam/localization.cpp:364-410, and its callers :127-135, :216-224):
+ * fls_set_global_map keeps the global map resident in device memory; fls_update_local_map(T) re-cuts the local map — a +-100 m
+ * pcl::CropBox around the translation of T, input order kept — when there is none yet or the pose is within 50 m of one of its
+ * edges, and hands it to AddCloudToLocalMap of the handle's plug-in without a host round trip.  *updated = 1 when a new local map
+ * was cut (need_update_local_map_), *n_local its size (0: LoadLocalMap returned an empty cloud; the matcher's map is untouched). */
+int fls_set_global_map(fls_handle* h, const void* pts, size_t n, size_t stride_bytes);
+int fls_update_local_map(fls_handle* h, const double T_colmajor[16], int* updated, size_t* n_local);
+
+/* PCD v0.7 files as pcl::io::loadPCDFile / savePCDFileBinary read and write them for x y z intensity clouds
+ * (include/common/keyframe.h:24-74, src/slam/localization.cpp:283-300): fls_pcd_read fills at most `capacity` packed
+ * x, y, z, intensity records (DATA ascii or binary; extra fields are skipped, a missing intensity reads 0) and returns the point
+ * count of the file in *n; fls_pcd_write writes DATA binary. */
+int fls_pcd_read(const char* path, float* xyzi, size_t capacity, size_t* n);
+int fls_pcd_write(const char* path, const float* xyzi, size_t n);
+
 /* IMU orientation samples around a scan — what LidarDistortionCorrector reads through its DataSearcher<IMUData>
  * (include/lidar/lidar_distortion_corrector.h:11-48, src/lidar/lidar_distortion_corrector.cpp:19-64): time stamps in microseconds
  * (ascending), unit quaternions in Eigen coefficient order x, y, z, w, the reference time of the scan (SetRefTime) and the
