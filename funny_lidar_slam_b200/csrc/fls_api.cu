@@ -19,6 +19,30 @@ void set_last_error(const std::string& s) { g_last_error = s; }
 const char* last_error_cstr() { return g_last_error.c_str(); }
 
 Handle::Handle(const fls_config& c) : cfg(c) {
+    try {
+        init();
+    } catch (...) {  // a throwing constructor does not run the destructor: give back what was acquired so far
+        release();
+        throw;
+    }
+}
+
+void Handle::release() {
+    if (h_state) cudaFreeHost(h_state);
+    if (h_batch) cudaFreeHost(h_batch);
+    h_state = nullptr;
+    h_batch = nullptr;
+    for (auto& e : prof_ev)
+        if (e) cudaEventDestroy(e);
+    prof_ev.clear();
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    ev0 = ev1 = nullptr;
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+}
+
+void Handle::init() {
     FLS_CUDA(cudaSetDevice(cfg.device));
     FLS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     FLS_CUDA(cudaEventCreate(&ev0));
@@ -51,7 +75,7 @@ Handle::Handle(const fls_config& c) : cfg(c) {
     }
     profile = (cfg.flags & FLS_FLAG_PROFILE) != 0;
     if (profile) {
-        prof_ev.resize(2 * (size_t)(cfg.max_iterations > 0 ? cfg.max_iterations : 1));
+        prof_ev.assign(2 * (size_t)(cfg.max_iterations > 0 ? cfg.max_iterations : 1), nullptr);
         for (auto& e : prof_ev) FLS_CUDA(cudaEventCreate(&e));
     }
     if (cfg.flags & FLS_FLAG_ITER_LOG) {
@@ -64,12 +88,7 @@ Handle::Handle(const fls_config& c) : cfg(c) {
 Handle::~Handle() {
     cudaSetDevice(cfg.device);
     if (stream) cudaStreamSynchronize(stream);
-    if (h_state) cudaFreeHost(h_state);
-    if (h_batch) cudaFreeHost(h_batch);
-    for (auto& e : prof_ev) cudaEventDestroy(e);
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
-    if (stream) cudaStreamDestroy(stream);
+    release();
 }
 
 // Copy a caller cloud (host memory, `stride` bytes per record) into a packed float4 device buffer.

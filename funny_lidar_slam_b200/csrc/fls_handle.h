@@ -94,6 +94,8 @@ struct Handle {
 
     explicit Handle(const fls_config& c);
     ~Handle();
+    void init();     // body of the constructor
+    void release();  // streams, events, pinned memory
     Handle(const Handle&) = delete;
     Handle& operator=(const Handle&) = delete;
 

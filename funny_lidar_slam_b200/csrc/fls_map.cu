@@ -10,6 +10,7 @@
 // the candidates (IvoxMap::evict_lru, lru_simulate).
 #include <cub/cub.cuh>
 
+#include <cstdlib>
 #include <functional>
 #include <queue>
 #include <vector>
@@ -44,9 +45,18 @@ bool lru_simulate(size_t size0, size_t capacity, const std::vector<unsigned>& ca
     return true;
 }
 
-BuildScratch::BuildScratch() { cudaMallocHost(&h_num_runs, sizeof(int)); }
+BuildScratch::BuildScratch() {
+    if (cudaMallocHost(&h_num_runs, sizeof(int)) != cudaSuccess) {  // no device / out of pinned memory: a plain allocation still works as a copy target
+        cudaGetLastError();
+        h_num_runs = static_cast<int*>(std::malloc(sizeof(int)));
+        pinned = false;
+    }
+}
 BuildScratch::~BuildScratch() {
-    if (h_num_runs) cudaFreeHost(h_num_runs);
+    if (h_num_runs) {
+        if (pinned) cudaFreeHost(h_num_runs);
+        else std::free(h_num_runs);
+    }
 }
 
 namespace {

@@ -24,7 +24,8 @@ struct BuildScratch {
     DevBuf<unsigned char> cub_tmp;
     DevBuf<float> minmax;
     DevBuf<int> num_runs;
-    int* h_num_runs = nullptr;  // pinned
+    int* h_num_runs = nullptr;  // pinned (plain memory when the pinned allocation failed)
+    bool pinned = true;
     BuildScratch();
     ~BuildScratch();
 };

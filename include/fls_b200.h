@@ -167,7 +167,10 @@ int fls_match(fls_handle* h, const void* ordered, size_t n_ordered, const void* 
               size_t stride_bytes, double T_colmajor[16], int* converged, fls_match_stats* stats);
 
 /* Same as fls_match but the scan is already resident in device memory as packed float4 {x,y,z,i}
- * (the `value` leg of bench.py).  `d_points` is a device pointer on the handle's device. */
+ * (the `value` leg of bench.py).  `d_points` is a device pointer on the handle's device.  The LOAM plug-ins keep the pointer for a
+ * later fls_fitness (the source cloud of the last Match, as upstream keeps source_cloud_ptr_): the buffer must stay valid and
+ * unchanged until the next Match on the handle, or fls_fitness must not be called.  `stats` (here and in every Match entry) is
+ * meaningful only when the call returns FLS_OK. */
 int fls_match_device(fls_handle* h, const void* d_points, size_t n, double T_colmajor[16], int* converged, fls_match_stats* stats);
 
 /* GetFitnessScore(max_range): FLT_MAX when unsupported / no inliers, as upstream. */

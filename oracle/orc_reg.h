@@ -193,6 +193,11 @@ private:
             const P4 q = transform_point_d(sp, T_);  // :265-266
             P4 nn[5];
             const int found = ivox_->closest(q, 5, 5.0f, nn);  // :269
+            // DELIBERATE DEVIATION: upstream's IVoxMap::GetClosestPoint returns false WITHOUT clearing `closest_pt`
+            // when the stencil holds no candidate at all (ivox_map.cpp:21-23), so nearest_points_[i] keeps what index i found in an
+            // earlier iteration — or in an earlier Match, where index i was a different point — and a plane is fitted to those
+            // stale neighbours.  Here (and on the GPU) a point without candidates has no neighbours: it is skipped, and the
+            // mapping-mode insertion rule adds it unconditionally (:93-96).  tests/test_gpu_p2plane.py isolates the case.
             nearest_[i].assign(nn, nn + found);
             if (found < 5) continue;  // :271-273
             double A[15];

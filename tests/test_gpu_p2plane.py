@@ -266,3 +266,35 @@ def test_batch_begin_end_on_two_handles(world, traj):
     for b in range(4):
         assert np.array_equal(out[b][0], ref[b][0]), b
         assert np.allclose(out[b][1], ref[b][1], rtol=0, atol=1e-12), b
+
+
+def test_point_without_candidates_is_skipped_not_stale(scene16):
+    """The documented deviation from upstream's stale nearest_points_ (ivox_map.cpp:21-23: GetClosestPoint leaves the output vector
+    untouched when the stencil is empty): a point whose stencil holds no map point contributes nothing — even when the same index
+    had five neighbours in the previous Match — on the GPU exactly as in the oracle."""
+    from funny_lidar_slam_b200._abi import FLS_FLAG_ITER_LOG
+    from funny_lidar_slam_b200.registration import PointcloudCluster, Registration
+    from oracle import pyoracle as orc
+    cfg = default_config(FLS_P2PLANE_IVOX, flags=FLS_FLAG_ITER_LOG)
+    g, o = Registration(cfg), orc.Registration(cfg)
+    g.AddCloudToLocalMap([scene16["map"]])
+    o.add_cloud(scene16["map"])
+    scan = scene16["scan"]
+    T = scene16["guess_small"].copy()
+    assert g.Match(PointcloudCluster(planar_cloud=scan), T)  # every index now "has" neighbours upstream
+    o.match(scan, scene16["guess_small"])
+    far = scan.copy()
+    far[::7, :3] += np.float32(900.0)  # every 7th index: far outside the map, no stencil candidate at any iteration
+    kept = np.ascontiguousarray(np.delete(scan, np.s_[::7], axis=0))
+    Tf, Tk = scene16["guess_small"].copy(), scene16["guess_small"].copy()
+    ok_f = g.Match(PointcloudCluster(planar_cloud=far), Tf)
+    st_f, log_f = g.last_stats, g.iter_log()
+    ok_k = g.Match(PointcloudCluster(planar_cloud=kept), Tk)
+    st_k, log_k = g.last_stats, g.iter_log()
+    ok_o, To, st_o = o.match(far, scene16["guess_small"])
+    assert ok_f == ok_k == ok_o and st_f.iterations == st_k.iterations == st_o.iterations
+    assert st_f.n_valid == st_k.n_valid == st_o.n_valid
+    for a, b in zip(log_f, log_k):  # the far points add nothing to H and g
+        assert np.allclose(a["H"], b["H"], rtol=1e-9, atol=1e-6) and np.allclose(a["g"], b["g"], rtol=1e-9, atol=1e-6)
+    dt, dr = synth.pose_error(Tf, To)
+    assert dt < POS_TOL and dr < ROT_TOL
