@@ -320,6 +320,38 @@ def secondary_kernels(device: int, peak: float, log, steps: int = 6):
                      "cpu_oracle_scans_per_s": 3 / t_cpu, "cpu_threads": orc.num_threads(), "map_points": int(len(mp)), "l2": "warm",
                      "parity": {k: par[k] for k in ("max_dpos_m", "max_drot_rad", "iters_equal", "converged_equal", "ok")}}
         log(f"secondary {name}: {out[name]}")
+    # mapping mode — the reference frontend's default (frontend.cpp:30-88): one scan per call, the map grows with every Match
+    # (LOAM-iVox: cached-5-NN insertion rule + incremental iVox insert; NDT: UpdateVoxel), GPU and oracle each on their own stream
+    from funny_lidar_slam_b200.registration import PointcloudCluster
+    stream_traj = synth.trajectory(64)
+    for name, method, sensor, extra in (("p2plane_ivox_64_stream", _abi.FLS_P2PLANE_IVOX, "hdl64", {}),
+                                        ("ndt_64_stream", _abi.FLS_NDT, "hdl64", {})):
+        n_stream = 12
+        cfg = _abi.default_config(method, device=device, localization_mode=0, **extra)
+        reg, oreg = Registration(cfg), orc.Registration(_abi.default_config(method, localization_mode=0, **extra))
+        first = synth.transform_points(synth.make_scan(world, stream_traj[0], sensor, seed=500)["points"], stream_traj[0])
+        reg.AddCloudToLocalMap([first])
+        oreg.add_cloud(first)
+        g_ms, o_ms, dpos, its = [], [], 0.0, 0
+        for k in range(1, n_stream + 1):
+            scan = synth.make_scan(world, stream_traj[k], sensor, seed=500 + k)["points"]
+            guess = synth.perturb_pose(stream_traj[k], seed=1500 + k, dpos=0.05, drot_deg=0.5)
+            T = guess.copy()
+            cl = PointcloudCluster(planar_cloud=scan) if method == _abi.FLS_P2PLANE_IVOX else PointcloudCluster(ordered_cloud=scan)
+            t0 = time.perf_counter()
+            reg.Match(cl, T)
+            g_ms.append((time.perf_counter() - t0) * 1e3)
+            its += reg.last_stats.iterations
+            ok, To, st = oreg.match(scan, guess)
+            o_ms.append(oreg.last_seconds * 1e3)
+            dpos = max(dpos, synth.pose_error(T, To)[0])
+        mi = reg.map_info()
+        out[name] = {"scans": n_stream, "ms_per_match_wall_incl_h2d_and_map_update": float(np.mean(g_ms[2:])), "mean_gn_iters": its / n_stream,
+                     "cpu_oracle_ms_per_match": float(np.mean(o_ms[2:])), "cpu_threads": orc.num_threads(), "map_points_end": int(mi.n_points),
+                     "map_voxels_end": int(mi.n_voxels), "incremental_inserts": int(mi.incremental_inserts), "full_builds": int(mi.full_builds),
+                     "max_dpos_vs_oracle_m": float(dpos), "voxels_equal_at_end": bool(mi.n_voxels == oreg.map_voxels)}
+        log(f"secondary {name}: {out[name]}")
+        del reg, oreg
     fx = FeatureExtractor(1.0, 0.1, device=device)
     shapes = {"features_livox_shaped": dict(kind="livox", seed=13, samples=65000),
               "features_hdl64_shaped": dict(kind="spinning", seed=13, sensor="hdl64")}

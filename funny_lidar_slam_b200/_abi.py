@@ -67,7 +67,8 @@ class FlsIterLog(C.Structure):
 
 
 class FlsMapInfo(C.Structure):
-    _fields_ = [("n_points", C.c_int64), ("n_voxels", C.c_int64), ("table_slots", C.c_int64), ("bytes", C.c_int64)]
+    _fields_ = [("n_points", C.c_int64), ("n_voxels", C.c_int64), ("table_slots", C.c_int64), ("bytes", C.c_int64),
+                ("incremental_inserts", C.c_int64), ("full_builds", C.c_int64)]
 
 
 class FlsFeatureCfg(C.Structure):

@@ -52,6 +52,7 @@ void Handle::init() {
     fit_out.reserve(2);
     ivox.set_resolution(cfg.ivox_resolution);
     ivox.key_mode = 0;
+    ivox.incremental = cfg.method == FLS_P2PLANE_IVOX && !cfg.localization_mode;  // mapping mode: the map grows by small inserts
     {
         static const int counts[4] = {1, 7, 19, 27};
         ivox.n_stencil = counts[cfg.ivox_nearby];
@@ -1436,6 +1437,8 @@ int fls_get_map_info(const fls_handle* hh, fls_map_info* out) {
         out->n_voxels = (long long)h->ivox.n_vox;
         out->table_slots = h->ivox.n_pts ? (long long)h->ivox.mask + 1 : 0;
         out->bytes = (long long)h->ivox.bytes();
+        out->incremental_inserts = (long long)h->ivox.n_incremental;
+        out->full_builds = (long long)h->ivox.n_full;
     } else if (h->cfg.method == FLS_NDT) {
         out->n_voxels = (long long)h->ndt.n_vox;
         out->table_slots = (long long)h->ndt.slots;

@@ -207,6 +207,57 @@ __global__ void list_fill_kernel(const unsigned long long* __restrict__ centers,
     if (lane == 0) table_insert(ctab, cmask, pack_key(x, y, z), cstart[c], ccount[c]);
 }
 
+// ---- incremental insertion (log-structured): touched voxels and the centres around them are rewritten at the end of the arrays ----
+// per touched voxel (run of the NEW points): where it lives now, how long it becomes
+__global__ void inc_plan_kernel(const unsigned long long* __restrict__ run_morton, const unsigned* __restrict__ add_counts, int n_runs,
+                                const HashSlot* __restrict__ tab, unsigned mask, unsigned* __restrict__ old_start, unsigned* __restrict__ old_count,
+                                unsigned* __restrict__ new_count, int* n_created) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_runs) return;
+    int x, y, z;
+    morton_decode(run_morton[v], x, y, z);
+    unsigned st = 0, cnt = 0;
+    if (!table_find(tab, mask, pack_key(x, y, z), st, cnt)) {
+        cnt = 0;
+        atomicAdd(n_created, 1);
+    }
+    old_start[v] = st;
+    old_count[v] = cnt;
+    new_count[v] = cnt + add_counts[v];
+}
+// one warp per touched voxel: its old points, then the new ones in input order, move to the end of the point array
+__global__ void inc_move_kernel(const unsigned long long* __restrict__ run_morton, int n_runs, const unsigned* __restrict__ old_start,
+                                const unsigned* __restrict__ old_count, const unsigned* __restrict__ add_start, const unsigned* __restrict__ add_count,
+                                const unsigned* __restrict__ new_off, unsigned base, const unsigned* __restrict__ idx_sorted,
+                                const float4* __restrict__ pts_new, float4* __restrict__ pts, HashSlot* tab, unsigned mask) {
+    const int v = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (v >= n_runs) return;
+    const unsigned dst = base + new_off[v], oc = old_count[v], os = old_start[v], ac = add_count[v], as = add_start[v];
+    for (unsigned k = lane; k < oc; k += 32) pts[dst + k] = pts[os + k];
+    for (unsigned k = lane; k < ac; k += 32) pts[dst + oc + k] = pts_new[idx_sorted[as + k]];
+    if (lane == 0) {
+        int x, y, z;
+        morton_decode(run_morton[v], x, y, z);
+        table_insert(tab, mask, pack_key(x, y, z), dst, oc + ac);
+    }
+}
+__global__ void add_base_kernel(unsigned* __restrict__ a, int n, unsigned base) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += base;
+}
+// how many of the affected centres are not in the centre table yet
+__global__ void inc_new_centres_kernel(const unsigned long long* __restrict__ centers, int n, const HashSlot* __restrict__ ctab, unsigned cmask,
+                                       const unsigned* __restrict__ ccount, int* counters /*[0] new centres, [1..2] old list records (u64)*/) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    int x, y, z;
+    morton_decode(centers[c], x, y, z);
+    unsigned st, cnt;
+    if (!table_find(ctab, cmask, pack_key(x, y, z), st, cnt)) atomicAdd(counters, 1);
+    else atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), (unsigned long long)cnt);
+}
+
 __global__ void repack_kernel(const unsigned char* __restrict__ raw, size_t n, size_t stride, float4* __restrict__ out) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -269,7 +320,13 @@ int IvoxMap::sort_and_runs(size_t n, cudaStream_t st, int* runs_out) {
     sc.counts.reserve(n);
     sc.starts.reserve(n);
     sc.num_runs.reserve(2);
-    pts_sorted.reserve(n);
+    // mapping mode: room for the voxels the incremental inserts rewrite; buffers grow geometrically (a cudaFree + cudaMalloc of a
+    // few hundred MB costs milliseconds — more than the build itself)
+    if (incremental) {
+        if (n + n / 2 + 65536 > pts_sorted.cap) pts_sorted.reserve(3 * n + 65536);
+    } else {
+        pts_sorted.reserve(n);
+    }
     ivox_keys_kernel<<<grid_for(n, 256), 256, 0, st>>>(pts_all.p, n, inv_res, key_mode, sc.keys.p, sc.idx.p);
     size_t tmp1 = 0, tmp2 = 0, tmp3 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp1, sc.keys.p, sc.keys_sorted.p, sc.idx.p, sc.idx_sorted.p, (int)n, 0, 63, st);
@@ -293,16 +350,159 @@ int IvoxMap::sort_and_runs(size_t n, cudaStream_t st, int* runs_out) {
     return FLS_OK;
 }
 
+// Incremental insert (mapping mode): cost proportional to the inserted points and the centres around the voxels they touch
+// (<= n_stencil per voxel), not to the map.  Touched voxels are rewritten — old points, then the new ones in input order — at the
+// end of the point array and their table slots redirected; every centre whose stencil contains a touched voxel gets a fresh run
+// at the end of `lists` (same visit order as a full build: stencil order, insertion order inside a voxel) and its centre slot
+// redirected.  The space left behind is garbage until the next full build, which happens when the slack runs out, when a table
+// would exceed its load factor, when the garbage outweighs the live data, or when the LRU has to evict.
+// Returns 1 when the caller has to take the full path instead.
+int IvoxMap::append_incremental(const float4* d_new, size_t n_new, long long capacity, cudaStream_t st) {
+    if (!incremental || n_pts == 0 || n_stencil <= 0 || n_new == 0) return 1;
+    BuildScratch& sc = scratch;
+    const size_t S = (size_t)n_stencil;
+    // new points -> voxel runs (stable: input order inside a voxel)
+    sc.keys.reserve(n_new);
+    sc.keys_sorted.reserve(n_new);
+    sc.uniq.reserve(n_new);
+    sc.idx.reserve(n_new);
+    sc.idx_sorted.reserve(n_new);
+    sc.counts.reserve(n_new);
+    sc.starts.reserve(n_new);
+    sc.num_runs.reserve(4);
+    ivox_keys_kernel<<<grid_for(n_new, 256), 256, 0, st>>>(d_new, n_new, inv_res, key_mode, sc.keys.p, sc.idx.p);
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, sc.keys.p, sc.keys_sorted.p, sc.idx.p, sc.idx_sorted.p, (int)n_new, 0, 63, st);
+    cub::DeviceRunLengthEncode::Encode(nullptr, t2, sc.keys_sorted.p, sc.uniq.p, sc.counts.p, sc.num_runs.p, (int)n_new, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, t3, sc.counts.p, sc.starts.p, (int)n_new, st);
+    size_t tmp = t1 > t2 ? t1 : t2;
+    tmp = tmp > t3 ? tmp : t3;
+    sc.cub_tmp.reserve(tmp + 256);
+    size_t tb = sc.cub_tmp.cap;
+    FLS_CUDA(cub::DeviceRadixSort::SortPairs(sc.cub_tmp.p, tb, sc.keys.p, sc.keys_sorted.p, sc.idx.p, sc.idx_sorted.p, (int)n_new, 0, 63, st));
+    tb = sc.cub_tmp.cap;
+    FLS_CUDA(cub::DeviceRunLengthEncode::Encode(sc.cub_tmp.p, tb, sc.keys_sorted.p, sc.uniq.p, sc.counts.p, sc.num_runs.p, (int)n_new, st));
+    FLS_CUDA(cudaMemcpyAsync(sc.h_num_runs, sc.num_runs.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FLS_CUDA(cudaStreamSynchronize(st));
+    const int T = *sc.h_num_runs;  // touched voxels
+    tb = sc.cub_tmp.cap;
+    FLS_CUDA(cub::DeviceScan::ExclusiveSum(sc.cub_tmp.p, tb, sc.counts.p, sc.starts.p, T, st));
+    // plan: old location / length of every touched voxel, how many are created
+    inc_old_start.reserve((size_t)T + 1);
+    inc_old_count.reserve((size_t)T + 1);
+    inc_new_count.reserve((size_t)T + 1);
+    inc_new_off.reserve((size_t)T + 1);
+    lru_cnt.reserve(8);
+    FLS_CUDA(cudaMemsetAsync(lru_cnt.p, 0, 8 * sizeof(int), st));
+    inc_plan_kernel<<<grid_for((size_t)T, 256), 256, 0, st>>>(sc.uniq.p, sc.counts.p, T, table.p, mask, inc_old_start.p, inc_old_count.p, inc_new_count.p,
+                                                            lru_cnt.p);
+    tb = sc.cub_tmp.cap;
+    FLS_CUDA(cub::DeviceScan::ExclusiveSum(sc.cub_tmp.p, tb, inc_new_count.p, inc_new_off.p, T, st));
+    // affected centres: every centre whose stencil contains a touched voxel
+    const size_t n_keys = (size_t)T * S;
+    ckeys.reserve(n_keys);
+    ckeys_sorted.reserve(n_keys);
+    cuniq.reserve(n_keys);
+    center_keys_kernel<<<grid_for(n_keys, 256), 256, 0, st>>>(sc.uniq.p, T, n_stencil, ckeys.p);
+    size_t u1 = 0, u2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, u1, ckeys.p, ckeys_sorted.p, (int)n_keys, 0, 63, st);
+    cub::DeviceSelect::Unique(nullptr, u2, ckeys_sorted.p, cuniq.p, sc.num_runs.p + 1, (int)n_keys, st);
+    sc.cub_tmp.reserve((u1 > u2 ? u1 : u2) + 256);
+    tb = sc.cub_tmp.cap;
+    FLS_CUDA(cub::DeviceRadixSort::SortKeys(sc.cub_tmp.p, tb, ckeys.p, ckeys_sorted.p, (int)n_keys, 0, 63, st));
+    tb = sc.cub_tmp.cap;
+    FLS_CUDA(cub::DeviceSelect::Unique(sc.cub_tmp.p, tb, ckeys_sorted.p, cuniq.p, sc.num_runs.p + 1, (int)n_keys, st));
+    int hc[8];
+    unsigned last_off = 0, last_cnt = 0;
+    int n_aff = 0;
+    FLS_CUDA(cudaMemcpyAsync(hc, lru_cnt.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FLS_CUDA(cudaMemcpyAsync(&last_off, inc_new_off.p + (T - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    FLS_CUDA(cudaMemcpyAsync(&last_cnt, inc_new_count.p + (T - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    FLS_CUDA(cudaMemcpyAsync(&n_aff, sc.num_runs.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FLS_CUDA(cudaStreamSynchronize(st));
+    launches += 9;
+    const int n_created = hc[0];
+    const size_t moved = (size_t)last_off + last_cnt;  // points of the rewritten voxels
+    // has to take the full path: eviction, no room, table load
+    if (capacity > 0 && (long long)n_vox + n_created >= capacity) return 1;
+    if (pts_end + moved > pts_sorted.cap) return 1;
+    if (2 * (n_vox + (size_t)n_created) > (size_t)mask + 1) return 1;
+    // voxels first (the centre runs are gathered from their new locations)
+    inc_move_kernel<<<grid_for((size_t)T * 32, 256), 256, 0, st>>>(sc.uniq.p, T, inc_old_start.p, inc_old_count.p, sc.starts.p, sc.counts.p, inc_new_off.p,
+                                                                 (unsigned)pts_end, sc.idx_sorted.p, d_new, pts_sorted.p, table.p, mask);
+    // centre runs
+    ccount.reserve((size_t)n_aff + 1);
+    cstart.reserve((size_t)n_aff + 1);
+    list_count_kernel<<<grid_for((size_t)n_aff, 128), 128, 0, st>>>(cuniq.p, n_aff, n_stencil, table.p, mask, ccount.p);
+    FLS_CUDA(cudaMemsetAsync(lru_cnt.p, 0, 8 * sizeof(int), st));
+    inc_new_centres_kernel<<<grid_for((size_t)n_aff, 256), 256, 0, st>>>(cuniq.p, n_aff, ctab.p, cmask, ccount.p, lru_cnt.p);
+    size_t t4 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, t4, ccount.p, cstart.p, n_aff, st);
+    sc.cub_tmp.reserve(t4 + 256);
+    tb = sc.cub_tmp.cap;
+    FLS_CUDA(cub::DeviceScan::ExclusiveSum(sc.cub_tmp.p, tb, ccount.p, cstart.p, n_aff, st));
+    unsigned l_off = 0, l_cnt = 0;
+    FLS_CUDA(cudaMemcpyAsync(hc, lru_cnt.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FLS_CUDA(cudaMemcpyAsync(&l_off, cstart.p + (n_aff - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    FLS_CUDA(cudaMemcpyAsync(&l_cnt, ccount.p + (n_aff - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    FLS_CUDA(cudaStreamSynchronize(st));
+    const size_t run_total = (size_t)l_off + l_cnt;
+    const int n_new_centres = hc[0];
+    unsigned long long old_records = 0;
+    std::memcpy(&old_records, hc + 2, sizeof(old_records));
+    launches += 5;
+    // From here on the point array and the occupied table are already updated; if the lists do not fit, the caller's full build
+    // regenerates everything from pts_all (which it extends itself), so nothing is lost.
+    if (lists_end + run_total > lists.cap || lists_end + run_total > 0xfffffff0ull) return 1;
+    if (4 * (n_centers + (size_t)n_new_centres) > (size_t)cmask + 1) return 1;
+    add_base_kernel<<<grid_for((size_t)n_aff, 256), 256, 0, st>>>(cstart.p, n_aff, (unsigned)lists_end);
+    list_fill_kernel<<<grid_for((size_t)n_aff * 32, 256), 256, 0, st>>>(cuniq.p, n_aff, n_stencil, table.p, mask, pts_sorted.p, cstart.p, ccount.p, lists.p,
+                                                                       ctab.p, cmask);
+    FLS_CUDA(cudaGetLastError());
+    launches += 2;
+    // bookkeeping
+    pts_end += moved;
+    pts_garbage += moved - n_new;  // the old copies of the rewritten voxels
+    lists_end += run_total;
+    lists_garbage += (size_t)old_records;
+    n_pts += n_new;
+    n_vox += (size_t)n_created;
+    n_centers += (size_t)n_new_centres;
+    n_list += run_total - (size_t)old_records;
+    ++n_incremental;
+    return FLS_OK;
+}
+
 int IvoxMap::append_and_build(const float4* d_new, size_t n_new, long long capacity, cudaStream_t st) {
-    const size_t n_old = n_pts;
-    size_t n = n_old + n_new;
+    // mapping mode: append without touching the rest of the map whenever that is possible
+    if (incremental && n_pts > 0 && n_new > 0 && (lists_garbage < n_list + (n_list >> 1)) && (pts_garbage < 2 * n_pts)) {
+        // pts_all / stamp_all first (the full path and the LRU read them)
+        const size_t n_old0 = n_pts, n0 = n_old0 + n_new;
+        if (n0 <= pts_all.cap && (capacity <= 0 || n0 <= stamp_all.cap)) {
+            FLS_CUDA(cudaMemcpyAsync(pts_all.p + n_old0, d_new, n_new * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+            if (capacity > 0) {
+                ++call_no;
+                ivox_stamp_kernel<<<grid_for(n_new, 256), 256, 0, st>>>(stamp_all.p + n_old0, n_new, call_no << 32);
+            }
+            const int rc = append_incremental(d_new, n_new, capacity, st);
+            if (rc == FLS_OK) return FLS_OK;
+            if (rc < 0) return rc;
+            // full path below: pts_all / stamp_all already hold the new points
+            return build_full(n_old0, n0, capacity, st, /*appended=*/true);
+        }
+    }
+    return build_full(n_pts, n_pts + n_new, capacity, st, false, d_new, n_new);
+}
+
+int IvoxMap::build_full(size_t n_old, size_t n_in, long long capacity, cudaStream_t st, bool appended, const float4* d_new, size_t n_new) {
+    size_t n = n_in;
     if (n == 0) return FLS_OK;
     if (n > 0xfffffff0ull) return FLS_ERR_INVALID_ARG;
     const bool lru = capacity > 0;  // the iVox map proper (the search grids have no capacity)
     // grow pts_all (and the insertion stamps) preserving the old contents
     if (n > pts_all.cap) {
         DevBuf<float4> bigger;
-        bigger.reserve(n + n / 2);
+        bigger.reserve(incremental ? 3 * n : n + n / 2);
         if (n_old) FLS_CUDA(cudaMemcpyAsync(bigger.p, pts_all.p, n_old * sizeof(float4), cudaMemcpyDeviceToDevice, st));
         FLS_CUDA(cudaStreamSynchronize(st));
         std::swap(bigger.p, pts_all.p);
@@ -310,16 +510,18 @@ int IvoxMap::append_and_build(const float4* d_new, size_t n_new, long long capac
     }
     if (lru && n > stamp_all.cap) {
         DevBuf<unsigned long long> bigger;
-        bigger.reserve(n + n / 2);
+        bigger.reserve(incremental ? 3 * n : n + n / 2);
         if (n_old) FLS_CUDA(cudaMemcpyAsync(bigger.p, stamp_all.p, n_old * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
         FLS_CUDA(cudaStreamSynchronize(st));
         std::swap(bigger.p, stamp_all.p);
         std::swap(bigger.cap, stamp_all.cap);
     }
-    if (n_new) FLS_CUDA(cudaMemcpyAsync(pts_all.p + n_old, d_new, n_new * sizeof(float4), cudaMemcpyDeviceToDevice, st));
-    if (lru && n_new) {
-        ++call_no;
-        ivox_stamp_kernel<<<grid_for(n_new, 256), 256, 0, st>>>(stamp_all.p + n_old, n_new, call_no << 32);
+    if (!appended) {
+        if (n_new) FLS_CUDA(cudaMemcpyAsync(pts_all.p + n_old, d_new, n_new * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        if (lru && n_new) {
+            ++call_no;
+            ivox_stamp_kernel<<<grid_for(n_new, 256), 256, 0, st>>>(stamp_all.p + n_old, n_new, call_no << 32);
+        }
     }
     int runs = 0;
     int rc = sort_and_runs(n, st, &runs);
@@ -334,7 +536,8 @@ int IvoxMap::append_and_build(const float4* d_new, size_t n_new, long long capac
         if (rc != FLS_OK) return rc;
     }
     size_t slots = 1024;
-    while (slots < 2 * (size_t)runs) slots <<= 1;
+    while (slots < (incremental ? 4 : 2) * (size_t)runs) slots <<= 1;  // mapping mode: room for the voxels to come
+    if (incremental && slots <= (size_t)mask + 1 && table.cap >= (size_t)mask + 1 && (size_t)mask + 1 >= 2 * (size_t)runs) slots = (size_t)mask + 1;  // keep the table while it is big enough
     table.reserve(slots);
     mask = (unsigned)(slots - 1);
     table_clear_kernel<<<grid_for(slots, 256), 256, 0, st>>>(table.p, slots);
@@ -342,7 +545,10 @@ int IvoxMap::append_and_build(const float4* d_new, size_t n_new, long long capac
     FLS_CUDA(cudaGetLastError());
     n_pts = n;
     n_vox = (size_t)runs;
+    pts_end = n;
+    pts_garbage = 0;
     launches += 2;
+    ++n_full;
     if (n_stencil > 0) return build_stencil_lists(st);
     return FLS_OK;
 }
@@ -464,20 +670,29 @@ int IvoxMap::build_stencil_lists(cudaStream_t st) {
     // load factor <= 0.25: the centre table is probed once per point-iteration and a long linear-probing chain stalls
     // a whole warp, so it is kept sparser than the occupied table
     size_t slots = 1024;
-    while (slots < 4 * (size_t)nc) slots <<= 1;
+    while (slots < (incremental ? 8 : 4) * (size_t)nc) slots <<= 1;
+    if (incremental && slots <= (size_t)cmask + 1 && ctab.cap >= (size_t)cmask + 1 && (size_t)cmask + 1 >= 4 * (size_t)nc) slots = (size_t)cmask + 1;
     ctab.reserve(slots);
     cmask = (unsigned)(slots - 1);
-    lists.reserve(total);
+    if (incremental) {  // mapping mode: room for the runs the incremental inserts append, geometric growth
+        if (2 * total + 1048576 > lists.cap) lists.reserve(4 * total + 1048576);
+    } else {
+        lists.reserve(total);
+    }
     table_clear_kernel<<<grid_for(slots, 256), 256, 0, st>>>(ctab.p, slots);
     list_fill_kernel<<<grid_for((size_t)nc * 32, 256), 256, 0, st>>>(cuniq.p, nc, n_stencil, table.p, mask, pts_sorted.p, cstart.p, ccount.p, lists.p,
                                                                      ctab.p, cmask);
     FLS_CUDA(cudaGetLastError());
     n_centers = (size_t)nc;
     n_list = total;
+    lists_end = total;
+    lists_garbage = 0;
     launches += 7;
     // the transient key arrays are the largest buffers of the build; give them back
-    ckeys.release();
-    ckeys_sorted.release();
+    if (!incremental) {
+        ckeys.release();
+        ckeys_sorted.release();
+    }
     return FLS_OK;
 }
 

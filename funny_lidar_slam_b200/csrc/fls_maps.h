@@ -77,6 +77,14 @@ struct IvoxMap {
     size_t dump_keys(unsigned long long* h_out, size_t cap, cudaStream_t st);  // packed keys of the occupied voxels (tests)
     // append n points that are already on the device (packed float4) and rebuild; returns fls_status
     int append_and_build(const float4* d_new, size_t n_new, long long capacity, cudaStream_t st);
+    int build_full(size_t n_old, size_t n_in, long long capacity, cudaStream_t st, bool appended, const float4* d_new = nullptr, size_t n_new = 0);
+    int append_incremental(const float4* d_new, size_t n_new, long long capacity, cudaStream_t st);
+    // log-structured state of the incremental path (mapping mode)
+    bool incremental = false;          // set by the owner: the map grows by small inserts (mapping mode)
+    size_t pts_end = 0, pts_garbage = 0;      // used part of pts_sorted, dead records in it
+    size_t lists_end = 0, lists_garbage = 0;  // used part of lists, dead records in it
+    size_t n_incremental = 0, n_full = 0;     // how many inserts took which path
+    DevBuf<unsigned> inc_old_start, inc_old_count, inc_new_count, inc_new_off;
     int build_stencil_lists(cudaStream_t st);
     size_t bytes() const { return pts_all.bytes() + pts_sorted.bytes() + table.bytes() + lists.bytes() + ctab.bytes(); }
 };

@@ -147,6 +147,8 @@ typedef struct {
     int64_t n_voxels;    /* occupied voxels (iVox / NDT) or grid cells (ICP) */
     int64_t table_slots; /* open-addressing table size */
     int64_t bytes;       /* device bytes held by the map */
+    int64_t incremental_inserts; /* LOAM-iVox mapping mode: inserts that only rewrote the touched voxels and the centres around them */
+    int64_t full_builds;         /* ... and inserts (incl. the first) that rebuilt table + stencil lists from all points */
 } fls_map_info;
 
 /* Fill `cfg` with the parameter set the reference ships for `method` (config YAMLs). */

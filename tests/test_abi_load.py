@@ -40,7 +40,7 @@ def test_struct_sizes_match_header_layout():
     # layouts are fixed by the C header; these sizes are what gcc produces for it (checked by the build)
     assert C.sizeof(_abi.FlsMatchStats) == 72
     assert C.sizeof(_abi.FlsIterLog) == 8 * (36 + 6 + 6 + 1 + 1)
-    assert C.sizeof(_abi.FlsMapInfo) == 32
+    assert C.sizeof(_abi.FlsMapInfo) == 48
 
 
 def test_error_strings_and_invalid_args():

@@ -97,3 +97,40 @@ def test_ivox_add_points_crosses_capacity(world, traj):
         seen |= kg
         prev = kg
     assert evicted_any, "the stream never crossed the capacity: the test is not testing the eviction"
+
+
+def test_ivox_incremental_insert_equals_full_build(world, traj):
+    """Mapping-mode handles insert incrementally (touched voxels + the centres around them are rewritten at the end of the arrays,
+    cost independent of the map size).  After every insert the map must answer 5-NN queries exactly like the oracle's IVoxMap and
+    like a handle that rebuilds everything (localization-mode handle, same points through fls_ivox_add_points)."""
+    from funny_lidar_slam_b200.registration import Registration
+    from oracle import pyoracle as orc
+    clouds = [synth.transform_points(synth.make_scan(world, traj[k], "vlp16", seed=80 + k)["points"], traj[k]) for k in range(10)]
+    g_inc = Registration(default_config(FLS_P2PLANE_IVOX, localization_mode=0))
+    g_full = Registration(default_config(FLS_P2PLANE_IVOX))
+    o = orc.IVox(0.5, 2, 1000000)
+    rng = np.random.default_rng(9)
+    g_inc.AddCloudToLocalMap([clouds[0]])  # first cloud: full build
+    g_full.ivox_add_points(clouds[0])
+    o.add(clouds[0])
+    for k in range(1, 10):
+        c = clouds[k][rng.permutation(len(clouds[k]))][: 2000 + 1500 * k]  # inserts of growing size, scattered voxels
+        g_inc.ivox_add_points(c)
+        g_full.ivox_add_points(c)
+        o.add(c)
+        mi, mf = g_inc.map_info(), g_full.map_info()
+        assert mi.n_points == mf.n_points == o.num_points and mi.n_voxels == mf.n_voxels == o.num_voxels, k
+        assert _keyset(g_inc.voxel_keys()) == _keyset(g_full.voxel_keys()), k
+        q = c[rng.integers(0, len(c), 3000)] + rng.normal(0, 0.2, (3000, 4)).astype(np.float32)
+        pi, ni = g_inc.ivox_knn(q)
+        pf, nf = g_full.ivox_knn(q)
+        po, no = o.closest(q)
+        assert np.array_equal(ni, nf) and np.array_equal(ni, no), k
+        assert np.array_equal(pi, pf), k  # same candidate order -> identical answers, slot by slot
+        for i in range(0, 3000, 5):
+            a, b = pi[i, :ni[i], :3], po[i, :no[i], :3]
+            assert np.array_equal(a[np.lexsort(a.T)], b[np.lexsort(b.T)]), (k, i)
+    mi = g_inc.map_info()
+    # (the inserts here are large next to the young map, so its slack runs out a few times; a long stream settles on the incremental path)
+    assert mi.incremental_inserts >= 4 and mi.incremental_inserts + mi.full_builds == 10, (mi.incremental_inserts, mi.full_builds)
+    assert g_full.map_info().incremental_inserts == 0
