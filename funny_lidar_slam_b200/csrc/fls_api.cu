@@ -319,11 +319,13 @@ int Handle::enqueue_ivox_batch(int B, const float4* const* d_scans, const size_t
     if (profile) FLS_CUDA(cudaEventRecord(prof_ev[0], stream));
     a.tickets = nullptr;
     a.ticket_stride = 0;
+    a.abort_word = nullptr;
     if (use_v9) {  // chunk tickets of the dynamic work distribution: one counter per (scan, iteration)
         a.ticket_stride = cfg.max_iterations + 2;
-        tickets.reserve((size_t)B * a.ticket_stride);
-        FLS_CUDA(cudaMemsetAsync(tickets.p, 0, sizeof(unsigned) * (size_t)B * a.ticket_stride, stream));
+        tickets.reserve((size_t)B * a.ticket_stride + 4);
+        FLS_CUDA(cudaMemsetAsync(tickets.p, 0, sizeof(unsigned) * ((size_t)B * a.ticket_stride + 4), stream));
         a.tickets = tickets.p;
+        a.abort_word = tickets.p + (size_t)B * a.ticket_stride;
     }
     if (use_v9) launch_p2plane_v9(a, grid, stream);
     else launch_p2plane_loop(a, grid, stream);
@@ -339,6 +341,8 @@ int Handle::enqueue_ivox_batch(int B, const float4* const* d_scans, const size_t
         FLS_CUDA(cudaMemcpyAsync(h_log.data(), log.p, sizeof(fls_iter_log) * log_cap, cudaMemcpyDeviceToHost, stream));
         d2h_bytes += (long long)(sizeof(fls_iter_log) * log_cap);
     }
+    h_abort = 0;
+    if (use_v9) FLS_CUDA(cudaMemcpyAsync(&h_abort, a.abort_word, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
     pend_n.assign(n, n + B);
     pend_v9 = use_v9;
     return FLS_OK;
@@ -351,6 +355,11 @@ int Handle::finish_ivox_batch(double* T, int* converged, fls_match_stats* st) {
     const size_t* n = pend_n.data();
     const bool use_v9 = pend_v9;
     end_call(st);
+    if (use_v9 && h_abort) {
+        pend_n.clear();
+        set_last_error("p2plane_v9_kernel: watchdog — a wait loop gave up after 4 s (hand-over protocol error)");
+        return FLS_ERR_CUDA;
+    }
     float kernel_ms = 0.f;
     if (profile) FLS_CUDA(cudaEventElapsedTime(&kernel_ms, prof_ev[0], prof_ev[1]));
     batch_n.assign(n, n + B);

@@ -46,6 +46,7 @@ struct P2PlaneLoopArgs {
     int visit_group;  // scans per visit (1..8): a warp works through its chunk of each of them between two CTA barriers
     unsigned* tickets;  // v9: chunk ticket counters [n_scans][ticket_stride], zeroed before the launch
     int ticket_stride;  // >= max_iterations + 2
+    unsigned* abort_word;  // v9 watchdog: zeroed before the launch, non-zero when a wait loop gave up (protocol error)
 };
 int p2plane_block();                   // threads per CTA of the selected kernel shape
 int p2plane_max_grid(int device);      // co-resident CTAs

@@ -43,6 +43,30 @@ __device__ __forceinline__ unsigned long long globaltimer_ns9() {
     return t;
 }
 
+// ---- watchdog: a protocol error must end the launch, never hang the device ------------------------------------------------
+// Every wait loop calls this about once per microsecond of waiting; a wait of more than kWatchdogNs raises the launch's abort word
+// (global memory, zeroed before the launch) and every loop of every warp leaves.  The host reports FLS_ERR_CUDA.
+constexpr unsigned long long kWatchdogNs = 4000000000ull;
+struct Watchdog {
+    unsigned long long t0 = 0;
+    unsigned n = 0;
+    __device__ __forceinline__ bool expired(unsigned* abort_word) {
+        if ((++n & 1023u) != 0u) return false;
+        if (*reinterpret_cast<volatile unsigned*>(abort_word)) return true;
+        const unsigned long long t = globaltimer_ns9();
+        if (!t0) t0 = t;
+        if (t - t0 > kWatchdogNs) {
+            atomicExch(abort_word, 1u);
+            return true;
+        }
+        return false;
+    }
+    __device__ __forceinline__ void reset() {
+        t0 = 0;
+        n = 0;
+    }
+};
+
 // ---- shared-memory primitives (PTX) ------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -464,9 +488,11 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) p2plane_v9_kernel(P2PlaneLoop
                 if (!avail && !cur_pending) {  // nothing to compute meanwhile: wait for the server (or for the end)
                     TRC_T0
                     unsigned ns = 32;
+                    Watchdog wd;
                     for (;;) {
                         avail = (int)(ld_acquire_smem(&ctl->ring_tail) - res) > 0;
                         if (avail || ld_acquire_smem(&ctl->quit)) break;
+                        if (wd.expired(a.abort_word)) break;
                         __nanosleep(ns);
                         if (ns < 256) ns <<= 1;
                     }
@@ -539,6 +565,7 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) p2plane_v9_kernel(P2PlaneLoop
             if (k < B) ++live;
         }
         unsigned tail = 0;
+        Watchdog wd;
         while (live > 0) {
             bool progress = false;
             // ---- pose records: all waiting slots polled with independent loads ---------------------------------------------
@@ -667,7 +694,14 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) p2plane_v9_kernel(P2PlaneLoop
                     }
                     const unsigned total = __shfl_sync(0xffffffffu, incl, kSlots - 1);
                     const unsigned excl = incl - (unsigned)cnt;
-                    for (int j = 0; j < cnt; ++j) ctl->ring[(tail + excl + (unsigned)j) & (kRing - 1)] = ((unsigned)my_s << 26) | (base + (unsigned)j);
+                    for (int j = 0; j < cnt; ++j) {
+                        ctl->ring[(tail + excl + (unsigned)j) & (kRing - 1)] = ((unsigned)my_s << 26) | (base + (unsigned)j);
+                        // the source points of a queued chunk are requested into this SM's L1 now: the compute warp that pops the
+                        // entry a few microseconds later finds them there (its prefetch stage executes in order and would wait)
+                        const char* sp = reinterpret_cast<const char*>(s_desc[my_s].src + ((size_t)(base + (unsigned)j) << 5));
+#pragma unroll
+                        for (int l = 0; l < 4; ++l) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + 128 * l));
+                    }
 #pragma unroll
                     for (int k = 0; k < kSlots; ++k) {
                         const unsigned c = __shfl_sync(0xffffffffu, (unsigned)cnt, k);
@@ -728,7 +762,12 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) p2plane_v9_kernel(P2PlaneLoop
                 } while ((fin >> rs[k]) & 1ull);
                 rph[k] = 0;
             }
-            if (!progress) __nanosleep(64);
+            if (progress) {
+                wd.reset();
+            } else {
+                if (wd.expired(a.abort_word)) break;
+                __nanosleep(64);
+            }
         }
         __syncwarp();
         if (lane == 0) st_release_smem(&ctl->quit, 1u);
@@ -749,8 +788,10 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) p2plane_v9_kernel(P2PlaneLoop
         if (!leader && !any_mine) return;
         unsigned long long fin = 0;
         int left = B;
-        for (int it = 0; left > 0; ++it) {
-            for (int sx = 0; sx < B && left > 0; ++sx) {
+        Watchdog wd;
+        bool aborted = false;
+        for (int it = 0; left > 0 && !aborted; ++it) {
+            for (int sx = 0; sx < B && left > 0 && !aborted; ++sx) {
                 if ((fin >> sx) & 1ull) continue;
                 const bool mine = fold_cta(sx) == cta;
                 const int slot = sx & (kSlots - 1);
@@ -762,9 +803,22 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) p2plane_v9_kernel(P2PlaneLoop
                         stopped = true;
                         break;
                     }
-                    if (ld_acquire_smem(&ctl->opened[slot]) >= key) break;
+                    if (ld_acquire_smem(&ctl->opened[slot]) >= key) {
+                        // a LATER item of the slot may be what was opened (scans k, k + 8, ... share slot k): then either this item
+                        // was opened and closed before (rows exist) or the scan stopped — the server sets `fin` before it opens
+                        // anything later, so a second look at `fin` tells which
+                        const unsigned f2 = sx < 32 ? ld_acquire_smem(&ctl->fin_lo) : ld_acquire_smem(&ctl->fin_hi);
+                        if ((f2 >> (sx & 31)) & 1u) stopped = true;
+                        break;
+                    }
+                    if (wd.expired(a.abort_word)) {
+                        aborted = true;
+                        break;
+                    }
                     __nanosleep(64);
                 }
+                if (aborted) break;
+                wd.reset();
                 if (stopped) {
                     fin |= 1ull << sx;
                     --left;
@@ -784,8 +838,14 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) p2plane_v9_kernel(P2PlaneLoop
                             if (q < nr) ok = ll_load(rows + (size_t)q * 32, tag, v[q]) && ok;
                         }
                         if (__all_sync(0xffffffffu, ok)) break;
+                        if (wd.expired(a.abort_word)) {
+                            aborted = true;
+                            break;
+                        }
                         __nanosleep(64);
                     }
+                    if (aborted) break;
+                    wd.reset();
                     double acc = 0.0;
 #pragma unroll
                     for (int q = 0; q < kGroup; ++q) acc += v[q];
@@ -804,8 +864,14 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) p2plane_v9_kernel(P2PlaneLoop
                             if (q < NG) ok = ll_load(grows + (size_t)q * 32, tag, v[q]) && ok;
                         }
                         if (__all_sync(0xffffffffu, ok)) break;
+                        if (wd.expired(a.abort_word)) {
+                            aborted = true;
+                            break;
+                        }
                         __nanosleep(64);
                     }
+                    if (aborted) break;
+                    wd.reset();
                     double acc = 0.0;
 #pragma unroll
                     for (int q = 0; q < 16; ++q) acc += v[q];

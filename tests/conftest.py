@@ -15,6 +15,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run under gpurun / by the driver at round end)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A GPU test that does not come back (a persistent kernel waiting for a hand-over that never arrives) must fail, not hang the
+    box: pytest-timeout's thread method ends the process, which also ends the kernel.  (The batch kernel additionally carries a
+    device-side watchdog, fls_p2plane_v9.cu.)"""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(240, method="thread"))
+
+
 @pytest.fixture(scope="session")
 def world():
     from funny_lidar_slam_b200 import synth
