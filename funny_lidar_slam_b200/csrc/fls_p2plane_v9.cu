@@ -681,11 +681,11 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) p2plane_v9_kernel(P2PlaneLoop
                     }
                     // valid tickets of lane k's block: [base, min(base + kb, n))
                     int cnt = 0;
-                    if (my_n > 0) {
+                    if (kb > 0 && my_n > 0) {
                         const int hi = (int)base + kb < my_n ? (int)base + kb : my_n;
                         cnt = hi > (int)base ? hi - (int)base : 0;
                     }
-                    const bool now_exh = my_n > 0 && (int)base + kb >= my_n;
+                    const bool now_exh = kb > 0 && (int)base + kb >= my_n;  // (kb > 0: this lane drew; an EMPTY scan is exhausted by its first draw)
                     unsigned incl = (unsigned)cnt;
 #pragma unroll
                     for (int o = 1; o < kSlots; o <<= 1) {
@@ -717,7 +717,7 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) p2plane_v9_kernel(P2PlaneLoop
                     __syncwarp();
                     tail += total;
                     if (lane == 0) st_release_smem(&ctl->ring_tail, tail);
-                    progress = true;
+                    progress = progress || total > 0u;  // an empty draw is not progress (the watchdog must see a stuck item)
                 }
             }
             // ---- close: counter exhausted and every chunk drawn here is done -> CTA row (warp order), LL store, rows cleared ----
