@@ -306,10 +306,6 @@ int Handle::enqueue_ivox_batch(int B, const float4* const* d_scans, const size_t
         const char* e = std::getenv("FLS_VISIT_GROUP");
         const int v = e ? std::atoi(e) : 8;  // measured at batch 8: group 2 / 3 / 4 / 6 / 8 -> 783 / 734 / 703 / 724 / 687 us per launch
         a.visit_group = v < 1 ? 1 : (v > 8 ? 8 : v);
-        if (use_v9) {  // v9: the field carries experiment switches (FLS_K1_OPTS bit 0: single selection chain)
-            const char* o = std::getenv("FLS_K1_OPTS");
-            a.visit_group = o ? std::atoi(o) : 0;
-        }
     }
     // roofline accounting (SURVEY.md §8d, K1 — the REFERENCE algorithm's traffic): 16 B source point + n_stencil x 16 B
     // slot probes + 32 B persistent record per point-iteration, 16 B per map record resident in the stencil voxels.
