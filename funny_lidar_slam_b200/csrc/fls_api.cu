@@ -306,6 +306,11 @@ int Handle::enqueue_ivox_batch(int B, const float4* const* d_scans, const size_t
         const char* e = std::getenv("FLS_VISIT_GROUP");
         const int v = e ? std::atoi(e) : 8;  // measured at batch 8: group 2 / 3 / 4 / 6 / 8 -> 783 / 734 / 703 / 724 / 687 us per launch
         a.visit_group = v < 1 ? 1 : (v > 8 ? 8 : v);
+        if (use_v9) {  // v9 reads the field as tuning knobs of the server's refill policy (fls_p2plane_v9.cu); 0 = defaults
+            const char* t = std::getenv("FLS_K1_TGT");
+            const char* d = std::getenv("FLS_K1_SEC");
+            a.visit_group = ((t ? std::atoi(t) : 0) & 0xff) | (((d ? std::atoi(d) : 0) & 0xff) << 8);
+        }
     }
     // roofline accounting (SURVEY.md §8d, K1 — the REFERENCE algorithm's traffic): 16 B source point + n_stencil x 16 B
     // slot probes + 32 B persistent record per point-iteration, 16 B per map record resident in the stencil voxels.

@@ -566,6 +566,10 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) p2plane_v9_kernel(P2PlaneLoop
         }
         unsigned tail = 0;
         Watchdog wd;
+        // tuning knobs (P2PlaneLoopArgs::visit_group, unused by this generation otherwise): low byte = outstanding target with several
+        // scans open, in quarters of W (default 12 = 3 W); next byte = share divisor of the second-oldest scan (default 4)
+        const int tgt_q = (a.visit_group & 0xff) ? (a.visit_group & 0xff) : 12;
+        const int sec_div = ((a.visit_group >> 8) & 0xff) ? ((a.visit_group >> 8) & 0xff) : 4;
         while (live > 0) {
             bool progress = false;
             // ---- pose records: all waiting slots polled with independent loads ---------------------------------------------
@@ -647,7 +651,7 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) p2plane_v9_kernel(P2PlaneLoop
                     n_open += (rph[k] == 1 && !exh[k]) ? 1 : 0;
                 }
                 // (with several scans in flight one more chunk per warp waits on the ring: the refill takes a server pass)
-                const int target = n_open > 1 ? 3 * W : 2 * W;
+                const int target = n_open > 1 ? (tgt_q * W) / 4 : 2 * W;
                 if (n_open > 0 && (int)outstanding < target) {
                     const int want = target - (int)outstanding;
                     // Oldest item first: the scans of a batch start in phase, and drawing from all of them at the same rate keeps
@@ -666,7 +670,7 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) p2plane_v9_kernel(P2PlaneLoop
                             }
                         }
                     }
-                    const int kb1 = want, kb2 = want / 4 > 0 ? want / 4 : 1;
+                    const int kb1 = want, kb2 = want / sec_div > 0 ? want / sec_div : 1;
                     int kb = 0;
                     unsigned base = 0;
                     int my_n = 0, my_s = 0;
