@@ -47,7 +47,9 @@ void Handle::init() {
     FLS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     FLS_CUDA(cudaEventCreate(&ev0));
     FLS_CUDA(cudaEventCreate(&ev1));
-    FLS_CUDA(cudaMallocHost(&h_state, sizeof(GnState) * kMaxBatch));
+    FLS_CUDA(cudaMallocHost(&h_state, sizeof(GnState) * kMaxBatch + 64));
+    h_abort = reinterpret_cast<unsigned*>(h_state + kMaxBatch);  // pinned: a copy into pageable memory would make the enqueue wait for the kernel
+    *h_abort = 0;
     state.reserve(kMaxBatch);
     fit_out.reserve(2);
     ivox.set_resolution(cfg.ivox_resolution);
@@ -342,8 +344,8 @@ int Handle::enqueue_ivox_batch(int B, const float4* const* d_scans, const size_t
         FLS_CUDA(cudaMemcpyAsync(h_log.data(), log.p, sizeof(fls_iter_log) * log_cap, cudaMemcpyDeviceToHost, stream));
         d2h_bytes += (long long)(sizeof(fls_iter_log) * log_cap);
     }
-    h_abort = 0;
-    if (use_v9) FLS_CUDA(cudaMemcpyAsync(&h_abort, a.abort_word, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    *h_abort = 0;
+    if (use_v9) FLS_CUDA(cudaMemcpyAsync(h_abort, a.abort_word, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
     pend_n.assign(n, n + B);
     pend_v9 = use_v9;
     return FLS_OK;
@@ -356,7 +358,7 @@ int Handle::finish_ivox_batch(double* T, int* converged, fls_match_stats* st) {
     const size_t* n = pend_n.data();
     const bool use_v9 = pend_v9;
     end_call(st);
-    if (use_v9 && h_abort) {
+    if (use_v9 && *h_abort) {
         pend_n.clear();
         set_last_error("p2plane_v9_kernel: watchdog — a wait loop gave up after 4 s (hand-over protocol error)");
         return FLS_ERR_CUDA;

@@ -116,7 +116,7 @@ struct Handle {
     int finish_ivox_batch(double* T, int* converged, fls_match_stats* st);
     std::vector<size_t> pend_n;  // scans of the batch in flight (empty: none)
     bool pend_v9 = false;
-    unsigned h_abort = 0;  // watchdog word of the last v9 launch (read back with the states)
+    unsigned* h_abort = nullptr;  // watchdog word of the last v9 launch (pinned, behind h_state; read back with the states)
 
     int add_cloud_ndt(const float4* d_cloud, size_t n);
     int match_ndt(const float4* d_src, size_t n, double* T, int* converged, fls_match_stats* st);
