@@ -1,7 +1,7 @@
 // fls_api.cu — the C ABI of include/fls_b200.h: handle lifetime, host<->device staging and the host side of
 // each plug-in's Match / AddCloudToLocalMap / GetFitnessScore.  The Gauss-Newton loop itself runs on the
-// device (residual kernel + gn_solve kernel per iteration, convergence decided on the device); the host
-// enqueues the iteration cap and reads the ~1 KB state block back once.
+// device (one persistent kernel per Match or per batch: residuals, 6x6 reduction, solve, pose update and stop rule);
+// the host reads the ~1.8 KB state block of every scan back once.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>

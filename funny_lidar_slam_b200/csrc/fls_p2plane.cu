@@ -1,25 +1,27 @@
-// fls_p2plane.cu — K1 (+ fused K6): the whole LoamPointToPlaneIVOX Gauss-Newton loop as ONE persistent kernel.
+// fls_p2plane.cu — K1 (+ fused K6), generation 8: the whole LoamPointToPlaneIVOX Gauss-Newton loop as ONE persistent kernel with a
+// CTA barrier per visit.  It serves the single Match (fls_match / fls_match_device); batches run on generation 9
+// (fls_p2plane_v9.cu), which shares the per-point arithmetic (fls_knn.cuh, fls_plane.cuh).  This file also holds the per-batch query
+// preparation (prep kernel + radix sort + gather), the Match-internal insertion rule of mapping mode and the k-NN test entry.
 //
 // Per source point and iteration it fuses what LoamPointToPlaneIVOX::PlanerMatch / ::SumCoefficient do
 // (include/registration/loam_point_to_plane_ivox.h:256-340 upstream): transform with the current pose, bounded
-// 5-NN in the iVox map, least-squares plane through the 5 neighbours (column-pivoted Householder QR, fp64),
-// validity / near-point gates, J (6) and |d|, and the 21+6+2 Gauss-Newton sums; the CTA that finishes an iteration
-// last reduces the partial sums in a fixed order, solves the 6x6 system, updates the pose and applies the stop
-// rule (:167-203), then releases the other CTAs into the next iteration.  No host round trip inside a Match.
+// 5-NN in the iVox map, least-squares plane through the 5 neighbours (normal equations, column-pivoted Householder QR as the
+// fallback, fp64), validity / near-point gates, J (6) and |d|, and the 21+6+2 Gauss-Newton sums; the scan's folding CTA reduces
+// the CTA rows in a fixed order, solves the 6x6 system, updates the pose and applies the stop rule (:167-203), then publishes the
+// next pose.  No host round trip inside a Match.
 //
 // B200 mapping
-//   * grid = #SMs x resident CTAs, launched cooperatively only to guarantee co-residency; the scheduling unit is the
-//     WARP: each warp pulls 32-point chunks from an atomic counter (dense regions cost more than sparse ones) and
-//     there is no block-wide barrier inside the work loop;
-//   * every chunk writes its own row of 31 partial sums; the warp that completes a group of 32 chunks folds the group
-//     into one row, and the last CTA folds the ~100 group rows — all in fixed order, so the result does not depend
-//     on which warp processed which chunk (bitwise reproducible) and the serial tail is ~1 us;
-//   * iteration hand-over: arrive counter + release flag (one wait per iteration) instead of grid-wide barriers; the
-//     6x6 solve is a register-resident LDL^T (pivoting fallback for rank-deficient systems);
+//   * grid = the CTAs the scan's chunks need (one 24-warp CTA per SM, 768 threads, 80 registers) + the folding CTA, launched
+//     cooperatively only to guarantee co-residency; the scheduling unit is the WARP: warp w of CTA c works on 32-point chunk
+//     (c, w) of every scan of the visit group, a static round-robin (consecutive chunks stay in one CTA: Morton neighbours share
+//     candidate runs in L1);
+//   * a visit = one Gauss-Newton iteration of up to 8 scans: poses in (LL records), chunks, one __syncthreads, CTA rows out (LL
+//     records, no fence, no atomic); only the scan's folding CTA waits for the other rows — 24 warps x 8 loads in flight sweep
+//     them until every tag matches, sums in a fixed order (bitwise reproducible for a given grid), gn_step, next pose out;
 //   * queries are processed in Morton order of their voxel (sorted once per Match), so the lanes of a warp share
 //     centre voxels: the table probe and the candidate stream are the same addresses -> L1 broadcast, no divergence;
 //   * k-NN = 1 probe of the centre table + a streaming scan of that centre's contiguous stencil list (fls_ivox.cuh),
-//     top-5 kept by a branch-free compare-exchange chain (half of all candidates enter the top-5 at list lengths ~25);
+//     top-6 kept as quantised 32-bit keys with integer min/max, exact comparator for ambiguous queries (fls_knn.cuh);
 //   * the 29 sums are accumulated warp-transposed: each lane stages {J, |d|, flags} in shared memory and lane k then
 //     owns sum k (32 FMAs on broadcast LDS) — one register pair of accumulator state instead of 62, no shuffles;
 //   * state that survives across iterations [quirk 1, SURVEY.md §7]: upstream resets the valid flags once per Match

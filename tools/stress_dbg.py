@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""The batch of test_batch_stress_many_small_and_empty_scans (24 scans incl. empty ones, slots shared by three scans each) run
+three times with timings — the shape that once hung the v9 kernel (an empty scan never exhausted its ticket counter)."""
 import sys, time
 sys.path.insert(0, "/root/repo")
 import numpy as np
