@@ -90,6 +90,37 @@ def test_batch_and_projector_argument_checks():
     assert rc == _abi.FLS_ERR_INVALID_ARG  # stride 12 is neither layout
 
 
+def test_round2_entries_argument_checks():
+    """The entries added in round 2 reject bad arguments before any device work (and a missing device is reported, not hidden)."""
+    import numpy as np
+    L = _lib.lib()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    no, npl = C.c_size_t(0), C.c_size_t(0)
+    raw = np.zeros((4, 5), np.float32)
+    out = np.zeros((4, 4), np.float32)
+    # fls_preprocess: jump_span >= 1, leaf > 0, outputs required
+    assert L.fls_preprocess(0, vp(raw), C.c_size_t(4), None, C.c_float(1.0), C.c_float(50.0), 0, C.c_float(0.5), vp(out), C.byref(no), vp(out),
+                            C.byref(npl)) == _abi.FLS_ERR_INVALID_ARG
+    assert L.fls_preprocess(0, vp(raw), C.c_size_t(4), None, C.c_float(1.0), C.c_float(50.0), 4, C.c_float(0.0), vp(out), C.byref(no), vp(out),
+                            C.byref(npl)) == _abi.FLS_ERR_INVALID_ARG
+    assert L.fls_preprocess(0, vp(raw), C.c_size_t(4), None, C.c_float(1.0), C.c_float(50.0), 4, C.c_float(0.5), None, C.byref(no), vp(out),
+                            C.byref(npl)) == _abi.FLS_ERR_INVALID_ARG
+    if L.fls_device_count() < 1:
+        assert L.fls_preprocess(0, vp(raw), C.c_size_t(4), None, C.c_float(1.0), C.c_float(50.0), 4, C.c_float(0.5), vp(out), C.byref(no), vp(out),
+                                C.byref(npl)) == _abi.FLS_ERR_NO_DEVICE
+    # handle entries with a null handle / null outputs
+    assert L.fls_match_batch_begin(None, 1, None, None, 16, None) == _abi.FLS_ERR_INVALID_ARG
+    assert L.fls_match_batch_begin_device(None, 1, None, None, None) == _abi.FLS_ERR_INVALID_ARG
+    assert L.fls_match_batch_end(None, None, None, None) == _abi.FLS_ERR_INVALID_ARG
+    assert L.fls_ivox_add_points(None, None, 0, 16) == _abi.FLS_ERR_INVALID_ARG
+    assert L.fls_set_global_map(None, None, 0, 16) == _abi.FLS_ERR_INVALID_ARG
+    assert L.fls_update_local_map(None, None, None, None) == _abi.FLS_ERR_INVALID_ARG
+    assert L.fls_get_voxel_keys(None, None, 0, None) == _abi.FLS_ERR_INVALID_ARG
+    assert L.fls_get_map_points(None, None, 0, None) == _abi.FLS_ERR_INVALID_ARG
+    assert L.fls_pcd_read(None, None, 0, None) == _abi.FLS_ERR_INVALID_ARG
+    assert L.fls_pcd_write(None, None, 0) == _abi.FLS_ERR_INVALID_ARG
+
+
 def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
     """include/fls_b200.h must compile as C99 (the boundary is a C ABI) and gcc's struct layouts must be the ones the ctypes
     mirror (and therefore the tests and the bench) assume."""
