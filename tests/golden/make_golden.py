@@ -84,5 +84,32 @@ def main():
     print("golden vectors written to", OUT)
 
 
+def round2():
+    """Goldens of the round-2 oracle parts: de-skew / pre-processing / projector with de-skew (oracle/orc_deskew.h) and the LRU of the
+    iVox map (oracle/orc_ivox.h) on the seeded case of tests/test_oracle_deskew.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_deskew import make_case
+    raw, imu = make_case(n=6000, seed=0)
+    o_ord, o_pl = orc.preprocess(raw, imu, 2.0, 60.0, 4, 0.5)
+    rng = np.random.default_rng(1)
+    ring = rng.integers(0, 16, len(raw)).astype(np.int32)
+    pr = orc.project_imu(raw[:, :4], ring, raw[:, 4], imu, 16, 900, np.float32(2 * np.pi / 900), 2.0, 60.0)
+    np.savez(os.path.join(OUT, "deskew_case0.npz"), n_ordered=len(o_ord), n_planar=len(o_pl), ordered_first=o_ord[:16], ordered_last=o_ord[-16:],
+             ordered_checksum=float(np.sum(o_ord.astype(np.float64))), planar_checksum=float(np.sum(o_pl.astype(np.float64))),
+             proj_n=pr["n"], proj_checksum=float(np.sum(pr["ordered"].astype(np.float64))), proj_depth_checksum=float(np.sum(pr["depth"].astype(np.float64))),
+             proj_col_checksum=int(np.sum(pr["col"].astype(np.int64))), proj_row_start=pr["row_start"], proj_row_end=pr["row_end"])
+    # LRU: three clouds through an IVoxMap of 5000 voxels (the second and third cloud evict)
+    world = synth.make_world()
+    traj = synth.trajectory(16)
+    iv = orc.IVox(0.5, 2, 5000)
+    counts = []
+    for k in range(3):
+        c = synth.transform_points(synth.make_scan(world, traj[k], "vlp16", seed=60 + k)["points"], traj[k])
+        iv.add(c)
+        counts.append((iv.num_voxels, iv.num_points))
+    np.savez(os.path.join(OUT, "ivox_lru_cap5000.npz"), counts=np.array(counts, np.int64))
+
+
 if __name__ == "__main__":
     main()
+    round2()

@@ -117,3 +117,29 @@ def test_project_imu_matches_plain_projection_plus_deskew():
         qc = np_interp(imu, int(imu["ref_time_us"]) + int(np.float64(p[4]) * 1.0e6))
         c = np_rot(np_quat_mul(q_ref_inv, qc), T[:3, :3] @ p[:3].astype(np.float64) + T[:3, 3])
         assert np.abs(out["ordered"][k][:3] - c).max() < 2e-5
+
+
+def test_against_round2_goldens(world, traj):
+    """Regression anchors of the round-2 oracle parts (tests/golden/make_golden.py round2()): they pin the ORACLE, not the reference."""
+    import os
+
+    from funny_lidar_slam_b200 import synth
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "deskew_case0.npz"))
+    raw, imu = make_case(n=6000, seed=0)
+    o_ord, o_pl = orc.preprocess(raw, imu, 2.0, 60.0, 4, 0.5)
+    assert len(o_ord) == int(g["n_ordered"]) and len(o_pl) == int(g["n_planar"])
+    assert np.array_equal(o_ord[:16], g["ordered_first"]) and np.array_equal(o_ord[-16:], g["ordered_last"])
+    assert float(np.sum(o_ord.astype(np.float64))) == float(g["ordered_checksum"])
+    assert float(np.sum(o_pl.astype(np.float64))) == float(g["planar_checksum"])
+    ring = np.random.default_rng(1).integers(0, 16, len(raw)).astype(np.int32)
+    pr = orc.project_imu(raw[:, :4], ring, raw[:, 4], imu, 16, 900, np.float32(2 * np.pi / 900), 2.0, 60.0)
+    assert pr["n"] == int(g["proj_n"]) and float(np.sum(pr["ordered"].astype(np.float64))) == float(g["proj_checksum"])
+    assert float(np.sum(pr["depth"].astype(np.float64))) == float(g["proj_depth_checksum"]) and int(np.sum(pr["col"].astype(np.int64))) == int(g["proj_col_checksum"])
+    assert np.array_equal(pr["row_start"], g["proj_row_start"]) and np.array_equal(pr["row_end"], g["proj_row_end"])
+    lru = np.load(os.path.join(gold, "ivox_lru_cap5000.npz"))["counts"]
+    iv = orc.IVox(0.5, 2, 5000)
+    for k in range(3):
+        iv.add(synth.transform_points(synth.make_scan(world, traj[k], "vlp16", seed=60 + k)["points"], traj[k]))
+        assert (iv.num_voxels, iv.num_points) == tuple(lru[k]), k
+    assert lru[1][0] == 4999 and lru[0][0] < 4999  # the capacity is crossed by the second cloud
